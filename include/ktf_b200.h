@@ -1,0 +1,253 @@
+/*
+ * ktf_b200.h -- C ABI of libktf_b200.so: hand-written sm_100a CUDA kernels for the
+ * wav -> x-vector hot path of shahruk10/kaldi-tflite.
+ *
+ * The reference has no FFI of its own: its boundary is the tf.keras Layer protocol
+ * (SURVEY.md 8b).  Each entry point below therefore replaces the `call()` body of one
+ * reference layer (cited per function as file:line under
+ * /root/reference/kaldi_tflite/lib/), and is what a ctypes / cgo / JNI stub would bind.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative KTF_E* code on failure;
+ *     `ktf_last_error()` returns a thread-local message for the last failure.
+ *   - all `*_dev` pointers are device pointers on the current CUDA device, owned by
+ *     the caller (the Python host lets torch allocate them); `*_host` are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all work is
+ *     enqueued asynchronously on it, nothing synchronises.
+ *   - handles own only constant tables / packed weights on the device on which they
+ *     were created; they are immutable after creation and may be shared by threads.
+ *   - tensors are row-major, innermost dimension contiguous; float32 unless stated.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef KTF_B200_H_
+#define KTF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KTF_OK 0
+#define KTF_EINVAL (-1)    /* bad argument / unsupported configuration */
+#define KTF_ECUDA (-2)     /* CUDA runtime error (message has the cudaError string) */
+#define KTF_ENOMEM (-3)
+
+/* Thread-local description of the last error returned on this thread. */
+const char* ktf_last_error(void);
+/* ABI version of this header (major * 100 + minor). */
+int ktf_version(void);
+/* Compute capability of the current device as major*10+minor (e.g. 100), <0 on error. */
+int ktf_device_arch(void);
+/* Total number of kernel launches enqueued by this library since load (bench bookkeeping). */
+int64_t ktf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Front-end: Framing + Windowing + FilterBank + DCT/MFCC in ONE fused kernel.
+ * Replaces layers/dsp/framing.py:243-265, windowing.py:180-209, filterbank.py:225-242,
+ * dct.py:175-176 and mfcc.py:197-244.  Frames are never materialised in HBM.
+ * ---------------------------------------------------------------------------------- */
+
+enum { KTF_OUT_MFCC = 0, KTF_OUT_FBANK = 1, KTF_OUT_WINDOWED = 2 };
+
+typedef struct {
+  int32_t frame_width;      /* samples gathered per frame = 2*(frame_size/2) (framing.py:107-109) */
+  int32_t frame_shift;      /* samples between frame starts; == frame_width for pre-framed input */
+  int32_t fft_length;       /* next power of two >= frame_width (filterbank.py:133-136,156) */
+  int32_t num_mels;         /* columns of mel_bank */
+  int32_t num_ceps;         /* columns of dct (<= num_mels); ignored unless KTF_OUT_MFCC */
+  int32_t output;           /* KTF_OUT_* */
+  int32_t remove_dc_offset; /* windowing.py:186-189 */
+  int32_t raw_energy;       /* windowing.py:192-193 / :205-206 */
+  int32_t use_energy;       /* MFCC: coefficient 0 <- log-energy (mfcc.py:214-228);
+                               WINDOWED: also write log-energy */
+  int32_t use_power;        /* filterbank.py:234-235 */
+  int32_t use_log_fbank;    /* filterbank.py:239-240 */
+  int32_t apply_lifter;     /* mfcc.py:211-212 */
+  float preemphasis;        /* windowing.py:195-200; <= 0 disables */
+  float energy_floor;       /* lower clip of the LOG energy (windowing.py:177) */
+  float epsilon;            /* added before log (windowing.py:176, filterbank.py:240) */
+} ktf_frontend_cfg;
+
+typedef struct ktf_frontend ktf_frontend;
+
+/* Tables are the constants the reference layers precompute in build():
+ *   window_host   [frame_width]                       windowing.py:130-156
+ *   mel_bank_host [(fft_length/2+1) x num_mels]       filterbank.py:141-189 (may be NULL for WINDOWED)
+ *   dct_host      [num_mels x num_ceps]               dct.py:98-143        (NULL unless MFCC)
+ *   lifter_host   [num_ceps]                          mfcc.py:146-159      (NULL unless apply_lifter)
+ * The bank is applied in sparse form: for every filter only the FFT bins between its first and
+ * last non-zero weight are visited. */
+int ktf_frontend_create(const ktf_frontend_cfg* cfg, const float* window_host,
+                        const float* mel_bank_host, const float* dct_host,
+                        const float* lifter_host, ktf_frontend** out);
+void ktf_frontend_destroy(ktf_frontend* fe);
+
+/* Frames produced for `num_samples` samples: 1 + (num_samples - frame_width) / frame_shift
+ * (framing.py:231-235), 0 if num_samples < frame_width. */
+int64_t ktf_frontend_num_frames(const ktf_frontend* fe, int64_t num_samples);
+/* Output feature dimension (num_ceps, num_mels or frame_width depending on `output`). */
+int32_t ktf_frontend_out_dim(const ktf_frontend* fe);
+
+/* Uniform batch: wav_dev[b * wav_stride + i], i < num_samples, b < batch.
+ * out_dev is (batch, T, out_dim) with T = ktf_frontend_num_frames(num_samples).
+ * energy_dev (batch, T) is written only for KTF_OUT_WINDOWED with use_energy (else may be NULL). */
+int ktf_frontend_forward(const ktf_frontend* fe, const float* wav_dev, int64_t batch,
+                         int64_t num_samples, int64_t wav_stride, float* out_dev,
+                         float* energy_dev, void* stream);
+
+/* Ragged batch: utterance b occupies wav_dev[sample_offsets[b] .. sample_offsets[b+1]) and its
+ * frames go to rows frame_offsets[b] .. frame_offsets[b+1]) of out_dev (total_frames, out_dim).
+ * Both offset arrays are HOST arrays of batch+1 int64 (frame_offsets is an OUTPUT, filled here). */
+int ktf_frontend_forward_ragged(const ktf_frontend* fe, const float* wav_dev, int64_t batch,
+                                const int64_t* sample_offsets_host, int64_t* frame_offsets_host,
+                                float* out_dev, float* energy_dev, void* stream);
+
+/* Framing alone (only when a caller really wants frames in HBM): out (batch, T, frame_width). */
+int ktf_framing_forward(const float* wav_dev, int64_t batch, int64_t num_samples,
+                        int64_t wav_stride, int32_t frame_width, int32_t frame_shift,
+                        float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * VAD -- layers/dsp/vad.py:156-203 (+ the gather_nd compaction of
+ * models/kaldi/xvector_extractor.py:163-165).  Integer-exact vote; the per-utterance mean
+ * log-energy is accumulated in a fixed order.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  float energy_threshold;
+  float energy_mean_scale;
+  float proportion_threshold;
+  int32_t frames_context;
+  int32_t energy_coeff;
+} ktf_vad_cfg;
+
+/* feats_dev (total_frames, dim); utterance b = rows frame_offsets_dev[b]..[b+1) (device int64,
+ * batch+1).  mask_dev (total_frames) float 0/1. */
+int ktf_vad_mask(const ktf_vad_cfg* cfg, const float* feats_dev, int32_t dim,
+                 const int64_t* frame_offsets_dev, int64_t batch, int64_t total_frames,
+                 float* mask_dev, void* stream);
+
+/* Stable compaction of the rows with mask != 0 (per utterance):
+ *   out_offsets_dev (batch+1 int64, device): compacted frame offsets,
+ *   index_dev (total_frames int64, device): row index (into feats) of each kept frame,
+ *   out_feats_dev (>= kept frames, dim) may be NULL to skip the gather.
+ * workspace_dev must hold ktf_vad_compact_workspace(batch, total_frames) bytes. */
+int64_t ktf_vad_compact_workspace(int64_t batch, int64_t total_frames);
+int ktf_vad_compact(const float* feats_dev, int32_t dim, const float* mask_dev,
+                    const int64_t* frame_offsets_dev, int64_t batch, int64_t total_frames,
+                    int64_t* out_offsets_dev, int64_t* index_dev, float* out_feats_dev,
+                    void* workspace_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Sliding-window CMVN -- layers/normalization/cmvn.py:186-250 (center=True only, like the
+ * reference).  in/out (total_frames, dim); ragged through frame_offsets_dev (batch+1).
+ * padding_valid: keep only frames [N/2, T-(N-1)/2) of each utterance longer than the
+ * window (cmvn.py:230-237); out rows then follow out_offsets_dev (batch+1, device).
+ * max_frames: any upper bound on the longest utterance (sizes the grid; the lengths themselves
+ * are read on the device, so a VAD-compacted batch needs no host round trip).
+ * ---------------------------------------------------------------------------------- */
+int ktf_cmvn_forward(const float* in_dev, int32_t dim, const int64_t* frame_offsets_dev,
+                     int64_t batch, int64_t total_frames, int64_t max_frames, int32_t window,
+                     int32_t norm_vars, int32_t padding_valid, const int64_t* out_offsets_dev,
+                     float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * TDNN affine (+ ReLU + BatchNorm + statistics) -- layers/tdnn/tdnn.py:251-280,
+ * keras ReLU (models/kaldi/sequential.py:71-72), layers/normalization/batchnorm.py:81-88,
+ * and the reduce-all branch of layers/stats/stats_pooling.py:211-240 fused as an epilogue.
+ *   y[t, u] = bn_scale[u] * act( sum_k sum_d x[clamp(t + ctx_k), d] * W[u, k*D + d] + bias[u] )
+ *             + bn_offset[u]
+ * ---------------------------------------------------------------------------------- */
+#define KTF_MAX_CONTEXT 16
+enum { KTF_PREC_F32 = 0, KTF_PREC_BF16 = 1 };
+enum { KTF_ACT_NONE = 0, KTF_ACT_RELU = 1 };
+
+typedef struct {
+  int32_t in_dim;                     /* D */
+  int32_t out_dim;                    /* U */
+  int32_t num_context;                /* K */
+  int32_t context[KTF_MAX_CONTEXT];   /* sorted offsets (tdnn.py:108) */
+  int32_t subsampling_factor;         /* tdnn.py:239 */
+  int32_t padding_valid;              /* 0 = SAME (edge clamp, tdnn.py:244-247), 1 = VALID */
+  int32_t activation;                 /* KTF_ACT_* applied before BatchNorm */
+  int32_t precision;                  /* KTF_PREC_* : operand precision of the contraction */
+} ktf_affine_cfg;
+
+typedef struct ktf_affine ktf_affine;
+
+/* weights_host: Kaldi <LinearParams> layout (U, K*D), i.e. W[u, k*D + d]
+ *   (layers/tdnn/utils.py:22-28 maps it to the TF kernel[0,k,d,u]);
+ * bias_host (U) or NULL; bn_scale_host/bn_offset_host (U) or NULL:
+ *   scale = gamma / sqrt(var + eps), offset = -mean * scale (batchnorm.py:81-88). */
+int ktf_affine_create(const ktf_affine_cfg* cfg, const float* weights_host, const float* bias_host,
+                      const float* bn_scale_host, const float* bn_offset_host, ktf_affine** out);
+void ktf_affine_destroy(ktf_affine* a);
+
+/* Rows produced for an utterance of T input rows (tdnn.py:224-239). */
+int64_t ktf_affine_out_rows(const ktf_affine* a, int64_t T);
+
+/* x_dev (total_in_rows, D); utterance b = rows in_offsets_dev[b]..[b+1); output rows follow
+ * out_offsets_dev (for SAME padding and subsampling 1 the two arrays are identical).
+ * y_dev (total_out_rows, U) may be NULL when only statistics are wanted.
+ * stats_dev, if not NULL, is (batch, 2, U) float32 and receives sum_t y and sum_t y^2 per
+ * utterance (it is zeroed by this call). */
+int ktf_affine_forward(const ktf_affine* a, const float* x_dev, const int64_t* in_offsets_dev,
+                       const int64_t* out_offsets_dev, int64_t batch, int64_t total_in_rows,
+                       int64_t total_out_rows, float* y_dev, float* stats_dev, void* stream);
+
+/* Element-wise helpers for callers that use ReLU / BatchNorm as stand-alone layers. */
+int ktf_relu_forward(const float* x_dev, int64_t n, float* y_dev, void* stream);
+int ktf_scale_offset_forward(const float* x_dev, int64_t rows, int32_t dim,
+                             const float* scale_dev, const float* offset_dev, float* y_dev,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * StatsPooling -- layers/stats/stats_pooling.py:211-316.
+ * ---------------------------------------------------------------------------------- */
+/* (batch, 2, U) sums -> (batch, U or 2U) mean || std; counts_dev = frames per utterance
+ * taken from offsets_dev (batch+1).  std = sqrt(relu(E[x^2]-mean^2) + eps). */
+int ktf_stats_finalize(const float* sums_dev, const int64_t* offsets_dev, int64_t batch,
+                       int32_t dim, int32_t include_std, float epsilon, int32_t input_period,
+                       float* out_dev, void* stream);
+/* General reduce-all (any input_period): x (total_rows, dim) -> out (batch, dim or 2*dim). */
+int ktf_stats_reduce(const float* x_dev, const int64_t* offsets_dev, int64_t batch, int32_t dim,
+                     int32_t input_period, int32_t include_std, float epsilon, float* out_dev,
+                     void* stream);
+/* Windowed mode for ONE uniform batch (batch, T, dim) -> (batch, T_out, dim or 2*dim);
+ * eval step t_j = t_start + j*output_period, window offsets range(left, right_excl, input_period),
+ * out-of-range taps masked (stats_pooling.py:179-209,266-295); repeat = output_period for SAME. */
+int ktf_stats_windows(const float* x_dev, int64_t batch, int64_t T, int32_t dim, int32_t left,
+                      int32_t right_excl, int32_t input_period, int64_t t_start, int64_t num_eval,
+                      int32_t output_period, int32_t repeat, int32_t include_std, float epsilon,
+                      float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * x-vector back-end -- models/kaldi/xvector_extractor.py:174-181:
+ *   y = (x - mean) @ L^T + o ; y *= sqrt(out_dim) / ||y||     transform (out_dim, in_dim+1) = [L | o]
+ * ---------------------------------------------------------------------------------- */
+int ktf_lda_forward(const float* x_dev, int64_t batch, int32_t in_dim, int32_t out_dim,
+                    const float* mean_dev, const float* transform_dev, int32_t length_norm,
+                    float* y_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * PLDA -- layers/plda/plda.py:163-263.  dtype_bytes = 4 (float32) or 8 (float64 parameters
+ * and arithmetic, the reference default).
+ * ---------------------------------------------------------------------------------- */
+typedef struct ktf_plda ktf_plda;
+int ktf_plda_create(int32_t dim, const double* mean_host, const double* transform_host,
+                    const double* psi_host, int32_t normalize_length, int32_t simple_length_norm,
+                    int32_t dtype_bytes, ktf_plda** out);
+void ktf_plda_destroy(ktf_plda* p);
+/* x (n, dim) float32 -> u (n, dim) of dtype_bytes each: u = T x - T m, length-normalised
+ * (plda.py:184-196). */
+int ktf_plda_transform(const ktf_plda* p, const float* x_dev, int64_t n, void* u_dev, void* stream);
+/* scores[i, j] = LLR(test u_i | enrolled u_j) (plda.py:215-245) for i < n_test, j < n_enroll;
+ * scores_dev is (n_test, ld) of dtype_bytes each.  Evaluated as A_i + B_j + u_i^T diag(c) u_j. */
+int ktf_plda_score(const ktf_plda* p, const void* u_test_dev, int64_t n_test,
+                   const void* u_enroll_dev, int64_t n_enroll, void* scores_dev, int64_t ld,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KTF_B200_H_ */

@@ -1,0 +1,59 @@
+"""Plumbing between user arrays (numpy / torch / DLPack) and raw device pointers."""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+
+
+def device():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def is_numpy_like(x):
+    return not isinstance(x, torch.Tensor) and not hasattr(x, "__dlpack__") or isinstance(x, np.ndarray)
+
+
+def as_device(x, dtype=torch.float32):
+    """numpy / list / torch (any device) / DLPack -> contiguous CUDA tensor of `dtype`."""
+    _native.require_cuda()
+    if isinstance(x, torch.Tensor):
+        t = x
+    elif isinstance(x, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    elif hasattr(x, "__dlpack__"):
+        t = torch.from_dlpack(x)
+    else:
+        t = torch.as_tensor(np.asarray(x))
+    return t.to(device=device(), dtype=dtype, non_blocking=True).contiguous()
+
+
+def ptr(t):
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def host_ptr(a):
+    """Pointer to a C-contiguous numpy array (kept alive by the caller)."""
+    if a is None:
+        return ctypes.c_void_p(0)
+    assert a.flags["C_CONTIGUOUS"]
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def like_input(out, ref):
+    """numpy in -> numpy out; everything else stays a CUDA torch tensor (DLPack-exportable)."""
+    if isinstance(ref, torch.Tensor) or (hasattr(ref, "__dlpack__") and not isinstance(ref, np.ndarray)):
+        return out
+    return out.cpu().numpy()
+
+
+def uniform_offsets(batch, rows):
+    return torch.arange(batch + 1, device=device(), dtype=torch.int64) * rows

@@ -1,0 +1,237 @@
+// PLDA transform + all-pairs log-likelihood-ratio scoring.
+//
+// Replaces layers/plda/plda.py:163-263 (under /root/reference/kaldi_tflite/lib/).
+// The reference materialises a (B, dim, B) broadcast tensor; here the score is evaluated in
+// its algebraically identical GEMM form:
+//     score[i, j] = A_i + B_j + sum_d u_i[d] * c[d] * u_j[d]
+//     r = psi/(psi+1), v1 = 1 + r, v0 = 1 + psi, c = r / v1
+//     A_i = sum_d u_i[d]^2 * (0.5/v0 - 0.5/v1) - 0.5 * (sum log v1 - sum log v0)
+//     B_j = -0.5 * sum_d (r u_j[d])^2 / v1
+// Arithmetic is fp32 or fp64 (the reference's default parameter dtype) per handle.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+struct ktf_plda {
+  int dim = 0;
+  int normalize_length = 1;
+  int simple_length_norm = 0;
+  int dtype_bytes = 4;
+  void* d_T = nullptr;       // (dim, dim)
+  void* d_offset = nullptr;  // (dim)  -T m
+  void* d_psi = nullptr;     // (dim)
+  void* d_c = nullptr;       // (dim)  r / v1
+  void* d_wa = nullptr;      // (dim)  0.5/v0 - 0.5/v1
+  void* d_wb = nullptr;      // (dim)  -0.5 r^2 / v1
+  double logdet_term = 0.0;  // -0.5 (sum log v1 - sum log v0)
+};
+
+namespace {
+
+template <typename T>
+struct CastLoad {  // float input rows promoted to the PLDA dtype
+  const float* p;
+  long long ld;
+  __device__ __forceinline__ T operator()(long long r, int k) const { return (T)p[r * ld + k]; }
+};
+
+template <typename T>
+struct OffsetEpi {
+  T* u;
+  const T* offset;
+  int dim;
+  __device__ __forceinline__ void operator()(long long row, long long col, T acc) const {
+    u[row * dim + col] = acc + offset[col];
+  }
+};
+
+template <typename T>
+struct ScaledLoad {
+  const T* p;
+  const T* c;
+  long long ld;
+  __device__ __forceinline__ T operator()(long long r, int k) const { return p[r * ld + k] * c[k]; }
+};
+
+template <typename T>
+struct ScoreEpi {
+  T* s;
+  const T* A;
+  const T* B;
+  long long ld;
+  __device__ __forceinline__ void operator()(long long row, long long col, T acc) const {
+    s[row * ld + col] = acc + A[row] + B[col];
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per vector: length normalisation (plda.py:163-196).
+template <typename T>
+__global__ void plda_norm_kernel(T* __restrict__ u, long long n, int dim, const T* __restrict__ psi,
+                                 int simple) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  T* p = u + row * dim;
+  T acc = T(0);
+  for (int d = lane; d < dim; d += 32) {
+    const T v = p[d];
+    acc += simple ? v * v : v * v / (psi[d] + T(1));
+  }
+  acc = warp_sum(acc);
+  const T nf = simple ? sqrt((T)dim) / sqrt(acc) : sqrt((T)dim / acc);
+  for (int d = lane; d < dim; d += 32) p[d] *= nf;
+}
+
+// One warp per vector: out[row] = sum_d w[d] * u[d]^2 + add
+template <typename T>
+__global__ void plda_quad_kernel(const T* __restrict__ u, long long n, int dim, const T* __restrict__ w,
+                                 T add, T* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const T* p = u + row * dim;
+  T acc = T(0);
+  for (int d = lane; d < dim; d += 32) acc += w[d] * p[d] * p[d];
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc + add;
+}
+
+template <typename T>
+int upload_as(void** dst, const std::vector<double>& v) {
+  std::vector<T> tmp(v.size());
+  for (size_t i = 0; i < v.size(); ++i) tmp[i] = (T)v[i];
+  return ktf::upload((T**)dst, tmp.data(), tmp.size());
+}
+
+template <typename T>
+int transform_impl(const ktf_plda* p, const float* x, int64_t n, T* u, cudaStream_t st) {
+  const int dim = p->dim;
+  CastLoad<T> al{x, (long long)dim};
+  ktf::DenseLoad<T> bl{(const T*)p->d_T, (long long)dim};
+  OffsetEpi<T> epi{u, (const T*)p->d_offset, dim};
+  dim3 grid((unsigned)((n + ktf::kTileM - 1) / ktf::kTileM), (unsigned)((dim + ktf::kTileN - 1) / ktf::kTileN));
+  ktf::gemm_nt_kernel<T><<<grid, ktf::kGemmThreads, 0, st>>>((long long)n, (long long)dim, dim, al, bl, epi);
+  KTF_LAUNCH_OK();
+  if (p->normalize_length) {
+    plda_norm_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(u, n, dim, (const T*)p->d_psi,
+                                                                 p->simple_length_norm);
+    KTF_LAUNCH_OK();
+  }
+  return KTF_OK;
+}
+
+template <typename T>
+int score_impl(const ktf_plda* p, const T* ut, int64_t nt, const T* ue, int64_t ne, T* scores, int64_t ld,
+               cudaStream_t st) {
+  const int dim = p->dim;
+  T* ab = nullptr;
+  KTF_CUDA(cudaMallocAsync((void**)&ab, (size_t)(nt + ne) * sizeof(T), st));
+  T* A = ab;
+  T* B = ab + nt;
+  plda_quad_kernel<T><<<(unsigned)((nt + 7) / 8), 256, 0, st>>>(ut, nt, dim, (const T*)p->d_wa,
+                                                                (T)p->logdet_term, A);
+  KTF_LAUNCH_OK();
+  plda_quad_kernel<T><<<(unsigned)((ne + 7) / 8), 256, 0, st>>>(ue, ne, dim, (const T*)p->d_wb, T(0), B);
+  KTF_LAUNCH_OK();
+  ScaledLoad<T> al{ut, (const T*)p->d_c, (long long)dim};
+  ktf::DenseLoad<T> bl{ue, (long long)dim};
+  ScoreEpi<T> epi{scores, A, B, (long long)ld};
+  dim3 grid((unsigned)((nt + ktf::kTileM - 1) / ktf::kTileM), (unsigned)((ne + ktf::kTileN - 1) / ktf::kTileN));
+  ktf::gemm_nt_kernel<T><<<grid, ktf::kGemmThreads, 0, st>>>((long long)nt, (long long)ne, dim, al, bl, epi);
+  KTF_LAUNCH_OK();
+  KTF_CUDA(cudaFreeAsync(ab, st));
+  return KTF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ktf_plda_create(int32_t dim, const double* mean_host, const double* transform_host,
+                    const double* psi_host, int32_t normalize_length, int32_t simple_length_norm,
+                    int32_t dtype_bytes, ktf_plda** out) {
+  KTF_CHECK_ARG(mean_host && transform_host && psi_host && out, "ktf_plda_create: null argument");
+  KTF_CHECK_ARG(dim > 0, "dim must be > 0");
+  KTF_CHECK_ARG(dtype_bytes == 4 || dtype_bytes == 8, "dtype_bytes must be 4 or 8");
+  ktf_plda* p = new ktf_plda();
+  p->dim = dim;
+  p->normalize_length = normalize_length;
+  p->simple_length_norm = simple_length_norm;
+  p->dtype_bytes = dtype_bytes;
+  const bool f32 = dtype_bytes == 4;
+  // Parameters are first rounded to the layer dtype, like tf.constant(..., dtype) (plda.py:103-105).
+  auto rnd = [&](double v) { return f32 ? (double)(float)v : v; };
+  std::vector<double> Tm((size_t)dim * dim), off(dim), psi(dim), c(dim), wa(dim), wb(dim);
+  for (size_t i = 0; i < Tm.size(); ++i) Tm[i] = rnd(transform_host[i]);
+  double ld1 = 0.0, ld0 = 0.0;
+  for (int r = 0; r < dim; ++r) {
+    double acc = 0.0;
+    for (int k = 0; k < dim; ++k) acc += Tm[(size_t)r * dim + k] * rnd(mean_host[k]);
+    off[r] = rnd(-acc);                                        // plda.py:116
+    psi[r] = rnd(psi_host[r]);
+    const double rr = psi[r] / (psi[r] + 1.0);                 // plda.py:228-231 with n = 1
+    const double v1 = 1.0 + rr, v0 = 1.0 + psi[r];
+    c[r] = rr / v1;
+    wa[r] = 0.5 / v0 - 0.5 / v1;
+    wb[r] = -0.5 * rr * rr / v1;
+    ld1 += log(v1);
+    ld0 += log(v0);
+  }
+  p->logdet_term = -0.5 * (ld1 - ld0);
+  int rc;
+  auto fail = [&](int code) { ktf_plda_destroy(p); return code; };
+#define UP(dst, vec)                                                          \
+  if ((rc = f32 ? upload_as<float>(&p->dst, vec) : upload_as<double>(&p->dst, vec)) != KTF_OK) return fail(rc)
+  UP(d_T, Tm);
+  UP(d_offset, off);
+  UP(d_psi, psi);
+  UP(d_c, c);
+  UP(d_wa, wa);
+  UP(d_wb, wb);
+#undef UP
+  *out = p;
+  return KTF_OK;
+}
+
+void ktf_plda_destroy(ktf_plda* p) {
+  if (!p) return;
+  cudaFree(p->d_T);
+  cudaFree(p->d_offset);
+  cudaFree(p->d_psi);
+  cudaFree(p->d_c);
+  cudaFree(p->d_wa);
+  cudaFree(p->d_wb);
+  delete p;
+}
+
+int ktf_plda_transform(const ktf_plda* p, const float* x_dev, int64_t n, void* u_dev, void* stream) {
+  KTF_CHECK_ARG(p && x_dev && u_dev, "ktf_plda_transform: null argument");
+  if (n <= 0) return KTF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->dtype_bytes == 4 ? transform_impl<float>(p, x_dev, n, (float*)u_dev, st)
+                             : transform_impl<double>(p, x_dev, n, (double*)u_dev, st);
+}
+
+int ktf_plda_score(const ktf_plda* p, const void* u_test_dev, int64_t n_test, const void* u_enroll_dev,
+                   int64_t n_enroll, void* scores_dev, int64_t ld, void* stream) {
+  KTF_CHECK_ARG(p && u_test_dev && u_enroll_dev && scores_dev, "ktf_plda_score: null argument");
+  KTF_CHECK_ARG(ld >= n_enroll, "ld must be >= n_enroll");
+  if (n_test <= 0 || n_enroll <= 0) return KTF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->dtype_bytes == 4
+             ? score_impl<float>(p, (const float*)u_test_dev, n_test, (const float*)u_enroll_dev, n_enroll,
+                                 (float*)scores_dev, ld, st)
+             : score_impl<double>(p, (const double*)u_test_dev, n_test, (const double*)u_enroll_dev,
+                                  n_enroll, (double*)scores_dev, ld, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,21 @@
+// Internal layout of the affine handle shared by the SIMT (tdnn.cu) and tcgen05 (tdnn_tc.cu) engines.
+#pragma once
+
+#include "common.cuh"
+
+struct ktf_affine {
+  ktf_affine_cfg cfg;
+  float* d_w = nullptr;       // (U, K*D) fp32, Kaldi layout
+  float* d_bias = nullptr;    // (U)
+  float* d_scale = nullptr;   // (U) BatchNorm scale, or null
+  float* d_offset = nullptr;  // (U) BatchNorm offset, or null
+  void* tc = nullptr;         // engine-private state of the tcgen05 path
+};
+
+namespace ktf {
+int affine_tc_prepare(ktf_affine* a, const float* weights_host);
+void affine_tc_release(ktf_affine* a);
+int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in_offsets_dev,
+                      const int64_t* out_offsets_dev, int64_t batch, int64_t total_in_rows,
+                      int64_t total_out_rows, float* y_dev, float* stats_dev, cudaStream_t st);
+}  // namespace ktf

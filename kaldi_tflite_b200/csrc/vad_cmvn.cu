@@ -1,0 +1,294 @@
+// Energy VAD (mask + stable compaction) and sliding-window CMVN for ragged batches.
+//
+// Replaces (file:line under /root/reference/kaldi_tflite/lib/):
+//   layers/dsp/vad.py:156-203, the tf.gather_nd compaction of
+//   models/kaldi/xvector_extractor.py:163-165, layers/normalization/cmvn.py:186-250.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double block_sum_double(double v, double* scratch) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < nw ? scratch[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) scratch[0] = t;
+  }
+  __syncthreads();
+  const double r = scratch[0];
+  __syncthreads();
+  return r;
+}
+
+// One CTA per utterance.
+__global__ void vad_mask_kernel(const float* __restrict__ feats, int dim, int coeff,
+                                const long long* __restrict__ offs, float thr0, float mean_scale,
+                                float prop_thr, int ctx, float* __restrict__ mask) {
+  __shared__ double scratch[32];
+  const long long r0 = offs[blockIdx.x];
+  const int T = (int)(offs[blockIdx.x + 1] - r0);
+  if (T <= 0) return;
+  const float* e = feats + r0 * dim + coeff;
+
+  float thr = thr0;
+  if (mean_scale > 0.0f) {  // vad.py:162-166 -- mean accumulated exactly (fp64), rounded once
+    double s = 0.0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) s += (double)e[(long long)t * dim];
+    s = block_sum_double(s, scratch);
+    const float mean = (float)(s / (double)T);
+    thr = thr0 + mean_scale * mean;
+  }
+  const int N = 2 * ctx + 1;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    bool keep;
+    if (ctx == 0) {
+      keep = e[(long long)t * dim] > thr;                     // vad.py:168-174
+    } else {
+      float count = 0.0f;                                     // conv1d, SAME zero padding (:180-182)
+      for (int k = -ctx; k <= ctx; ++k) {
+        const int u = t + k;
+        if (u >= 0 && u < T && e[(long long)u * dim] > thr) count += 1.0f;
+      }
+      float size = (float)N;                                  // edge window sizes (:124-135,187-193)
+      for (int i = 0; i < ctx; ++i) {                         // left edge: index i, size ctx+1+i
+        if (((i % T) + T) % T == t) size = (float)(ctx + 1 + i);
+      }
+      for (int i = 0; i < ctx; ++i) {                         // right edge: index -ctx+i, size 2ctx-i
+        const int idx = -ctx + i;
+        if ((((idx + T) % T) + T) % T == t) size = (float)(2 * ctx - i);
+      }
+      keep = __fdiv_rn(count, size) >= prop_thr;              // :197-199
+    }
+    mask[r0 + t] = keep ? 1.0f : 0.0f;
+  }
+}
+
+__global__ void vad_count_kernel(const float* __restrict__ mask, const long long* __restrict__ offs,
+                                 long long* __restrict__ counts) {
+  __shared__ double scratch[32];
+  const long long r0 = offs[blockIdx.x];
+  const int T = (int)(offs[blockIdx.x + 1] - r0);
+  double c = 0.0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) c += (mask[r0 + t] != 0.0f) ? 1.0 : 0.0;
+  c = block_sum_double(c, scratch);
+  if (threadIdx.x == 0) counts[blockIdx.x] = (long long)(c + 0.5);
+}
+
+// Single CTA: exclusive scan of counts -> out_offsets (batch + 1).
+__global__ void scan_counts_kernel(const long long* __restrict__ counts, long long batch,
+                                   long long* __restrict__ out_offsets) {
+  __shared__ long long s_part[1024];
+  __shared__ long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < batch; base += blockDim.x) {
+    const long long i = base + threadIdx.x;
+    const long long v = i < batch ? counts[i] : 0;
+    s_part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < blockDim.x; o <<= 1) {
+      long long add = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_part[threadIdx.x] += add;
+      __syncthreads();
+    }
+    const long long incl = s_part[threadIdx.x];
+    if (i < batch) out_offsets[i] = s_carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out_offsets[batch] = s_carry;
+}
+
+// One CTA per utterance: stable compaction of kept rows.
+__global__ void vad_compact_kernel(const float* __restrict__ feats, int dim,
+                                   const float* __restrict__ mask,
+                                   const long long* __restrict__ offs,
+                                   const long long* __restrict__ out_offs,
+                                   long long* __restrict__ index, float* __restrict__ out_feats) {
+  __shared__ int s_scan[256];
+  __shared__ int s_base;
+  const long long r0 = offs[blockIdx.x];
+  const int T = (int)(offs[blockIdx.x + 1] - r0);
+  const long long o0 = out_offs[blockIdx.x];
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int base = 0; base < T; base += blockDim.x) {
+    const int t = base + threadIdx.x;
+    const int keep = (t < T && mask[r0 + t] != 0.0f) ? 1 : 0;
+    s_scan[threadIdx.x] = keep;
+    __syncthreads();
+    for (int o = 1; o < blockDim.x; o <<= 1) {
+      const int add = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_scan[threadIdx.x] += add;
+      __syncthreads();
+    }
+    const int pos = s_base + s_scan[threadIdx.x] - keep;
+    if (keep) index[o0 + pos] = r0 + t;
+    const int chunk_total = s_scan[blockDim.x - 1];
+    if (out_feats != nullptr) {
+      // cooperative row copy: every thread helps copying the rows kept in this chunk
+      __syncthreads();
+      // reuse s_scan as a list of kept local t's
+      const int mypos = s_scan[threadIdx.x] - keep;
+      __syncthreads();
+      if (keep) s_scan[mypos] = t;
+      __syncthreads();
+      for (int e = threadIdx.x; e < chunk_total * dim; e += blockDim.x) {
+        const int rr = e / dim, d = e - rr * dim;
+        out_feats[(o0 + s_base + rr) * dim + d] = feats[(r0 + s_scan[rr]) * dim + d];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += chunk_total;
+    __syncthreads();
+  }
+}
+
+// Sliding CMVN.  blockDim = (32 feature lanes, 8 sub-chunks); each y-slice owns kSub consecutive
+// output frames of one utterance and carries the window sum along them.
+constexpr int kCmvnSub = 32;
+constexpr int kCmvnY = 8;
+
+__global__ void cmvn_kernel(const float* __restrict__ in, int dim, const long long* __restrict__ offs,
+                            int window, int norm_vars, int padding_valid,
+                            const long long* __restrict__ out_offs, float* __restrict__ out) {
+  // grid (batch, chunk groups); block (32 feature lanes, kCmvnY sub-chunks of kCmvnSub frames)
+  const long long b = blockIdx.x;
+  const long long r0 = offs[b];
+  const int T = (int)(offs[b + 1] - r0);
+  const int N = window;
+  // output frame range of this utterance (cmvn.py:230-237)
+  int ta = 0, tb = T;
+  if (padding_valid) {
+    ta = N / 2;
+    tb = T - (N - 1) / 2;
+    if (tb < 0) tb += T;            // python slice semantics for a negative stop
+    if (tb < 0) tb = 0;
+    if (tb > T) tb = T;
+    if (ta > tb) ta = tb;
+  }
+  const long long o0 = out_offs ? out_offs[b] : r0;
+  const int t0 = ta + (blockIdx.y * kCmvnY + threadIdx.y) * kCmvnSub;
+  const int t1 = min(t0 + kCmvnSub, tb);
+  if (t0 >= t1) return;
+  const float* x = in + r0 * dim;
+
+  for (int d = threadIdx.x; d < dim; d += 32) {
+    if (T <= N) {                                            // global stats (cmvn.py:214-222)
+      float s = 0.0f, s2 = 0.0f;
+      for (int t = 0; t < T; ++t) {
+        const float v = x[(long long)t * dim + d];
+        s += v;
+        s2 += __fmul_rn(v, v);
+      }
+      const float mean = s / (float)T;
+      float sd = 1.0f;
+      if (norm_vars) sd = sqrtf(s2 / (float)T - __fmul_rn(mean, mean));
+      for (int t = t0; t < t1; ++t) {
+        float v = x[(long long)t * dim + d] - mean;
+        if (norm_vars) v = v / sd;
+        out[(o0 + (t - ta)) * dim + d] = v;
+      }
+    } else {                                                 // sliding window (cmvn.py:172-204)
+      int ws = min(max(t0 - N / 2, 0), T - N);
+      float s = 0.0f, s2 = 0.0f;
+      for (int t = ws; t < ws + N; ++t) {
+        const float v = x[(long long)t * dim + d];
+        s += v;
+        s2 += __fmul_rn(v, v);
+      }
+      for (int t = t0; t < t1; ++t) {
+        const int want = min(max(t - N / 2, 0), T - N);
+        if (want != ws) {  // advances by exactly one
+          const float vo = x[(long long)ws * dim + d];
+          const float vn = x[(long long)(ws + N) * dim + d];
+          s += vn - vo;
+          s2 += __fmul_rn(vn, vn) - __fmul_rn(vo, vo);
+          ws = want;
+        }
+        const float mean = s / (float)N;
+        float v = x[(long long)t * dim + d] - mean;
+        if (norm_vars) v = v / sqrtf(s2 / (float)N - __fmul_rn(mean, mean));
+        out[(o0 + (t - ta)) * dim + d] = v;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ktf_vad_mask(const ktf_vad_cfg* cfg, const float* feats_dev, int32_t dim,
+                 const int64_t* frame_offsets_dev, int64_t batch, int64_t total_frames,
+                 float* mask_dev, void* stream) {
+  KTF_CHECK_ARG(cfg && feats_dev && frame_offsets_dev && mask_dev, "ktf_vad_mask: null argument");
+  KTF_CHECK_ARG(cfg->energy_mean_scale >= 0.0f, "`energy_mean_scale` must be >= 0");
+  KTF_CHECK_ARG(cfg->frames_context >= 0, "`frames_context` must be >= 0");
+  KTF_CHECK_ARG(cfg->proportion_threshold > 0.0f && cfg->proportion_threshold < 1.0f,
+                "`proportion_threshold` must be between 0 and 1 (exlcusive)");
+  KTF_CHECK_ARG(cfg->energy_coeff >= 0 && cfg->energy_coeff < dim, "energy_coeff out of range");
+  (void)total_frames;
+  if (batch <= 0) return KTF_OK;
+  vad_mask_kernel<<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>(
+      feats_dev, dim, cfg->energy_coeff, (const long long*)frame_offsets_dev, cfg->energy_threshold,
+      cfg->energy_mean_scale, cfg->proportion_threshold, cfg->frames_context, mask_dev);
+  KTF_LAUNCH_OK();
+  return KTF_OK;
+}
+
+int64_t ktf_vad_compact_workspace(int64_t batch, int64_t total_frames) {
+  (void)total_frames;
+  return (batch + 1) * (int64_t)sizeof(long long);
+}
+
+int ktf_vad_compact(const float* feats_dev, int32_t dim, const float* mask_dev,
+                    const int64_t* frame_offsets_dev, int64_t batch, int64_t total_frames,
+                    int64_t* out_offsets_dev, int64_t* index_dev, float* out_feats_dev,
+                    void* workspace_dev, void* stream) {
+  KTF_CHECK_ARG(mask_dev && frame_offsets_dev && out_offsets_dev && index_dev && workspace_dev,
+                "ktf_vad_compact: null argument");
+  KTF_CHECK_ARG(out_feats_dev == nullptr || feats_dev != nullptr, "feats_dev required for the gather");
+  (void)total_frames;
+  if (batch <= 0) return KTF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long* counts = (long long*)workspace_dev;
+  vad_count_kernel<<<(unsigned)batch, 256, 0, st>>>(mask_dev, (const long long*)frame_offsets_dev, counts);
+  KTF_LAUNCH_OK();
+  scan_counts_kernel<<<1, 1024, 0, st>>>(counts, batch, (long long*)out_offsets_dev);
+  KTF_LAUNCH_OK();
+  vad_compact_kernel<<<(unsigned)batch, 256, 0, st>>>(feats_dev, dim, mask_dev,
+                                                      (const long long*)frame_offsets_dev,
+                                                      (const long long*)out_offsets_dev,
+                                                      (long long*)index_dev, out_feats_dev);
+  KTF_LAUNCH_OK();
+  return KTF_OK;
+}
+
+int ktf_cmvn_forward(const float* in_dev, int32_t dim, const int64_t* frame_offsets_dev,
+                     int64_t batch, int64_t total_frames, int64_t max_frames, int32_t window,
+                     int32_t norm_vars, int32_t padding_valid, const int64_t* out_offsets_dev,
+                     float* out_dev, void* stream) {
+  KTF_CHECK_ARG(in_dev && frame_offsets_dev && out_dev, "ktf_cmvn_forward: null argument");
+  KTF_CHECK_ARG(window > 0, "`window` and `min_window` must be > 0");
+  KTF_CHECK_ARG(!padding_valid || out_offsets_dev, "out_offsets_dev is required for VALID padding");
+  if (batch <= 0 || total_frames <= 0 || max_frames <= 0) return KTF_OK;
+  const long long per_block = (long long)kCmvnY * kCmvnSub;
+  const long long gy = (max_frames + per_block - 1) / per_block;
+  KTF_CHECK_ARG(gy <= 65535, "max_frames too large for ktf_cmvn_forward");
+  cmvn_kernel<<<dim3((unsigned)batch, (unsigned)gy), dim3(32, kCmvnY), 0, (cudaStream_t)stream>>>(
+      in_dev, dim, (const long long*)frame_offsets_dev, window, norm_vars, padding_valid,
+      (const long long*)out_offsets_dev, out_dev);
+  KTF_LAUNCH_OK();
+  return KTF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+"""
+PLDA scoring layer with the reference's constructor surface
+(/root/reference/kaldi_tflite/lib/layers/plda/plda.py:41-263).
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from .. import _tensor as T
+from .base import Layer
+
+
+def _np_dtype(dtype):
+    if isinstance(dtype, torch.dtype):
+        return {torch.float32: np.float32, torch.float64: np.float64}[dtype]
+    name = getattr(dtype, "name", None) or str(dtype)
+    if "64" in name or name in ("double", "float"):
+        return np.float64
+    if "32" in name:
+        return np.float32
+    return np.dtype(dtype).type
+
+
+class PLDA(Layer):
+
+    def __init__(self, dim, plda_mean, plda_transform, plda_psi, normalize_length=True,
+                 simple_length_norm=False, dtype=np.float64, return_transformed=True, name=None):
+        super().__init__(name=name, trainable=False)
+        self.dim = int(dim)
+        self.normalizeLength = normalize_length
+        self.simpleLengthNorm = simple_length_norm
+        self.paramDtype = _np_dtype(dtype)
+        if self.paramDtype not in (np.float32, np.float64):
+            raise ValueError("dtype must be float32 or float64")
+        self.returnTransformed = return_transformed
+        self.mean = np.ascontiguousarray(plda_mean, dtype=np.float64)
+        self.transformMat = np.ascontiguousarray(plda_transform, dtype=np.float64)
+        self.psi = np.ascontiguousarray(plda_psi, dtype=np.float64)
+        self.assertParamShapes()
+        self.inputRank = 3
+        self._handle = None
+
+    def assertParamShapes(self):
+        assert self.mean.ndim == 1, f"plda_mean must be a vector, got dimension={self.mean.ndim}"
+        assert self.psi.ndim == 1, f"plda_psi must be a vector, got dimension={self.psi.ndim}"
+        assert self.transformMat.ndim == 2, \
+            f"plda_transform_mat must be a matrix, got dimension={self.transformMat.ndim}"
+        assert self.mean.shape[0] == self.dim, \
+            f"plda_mean dimension size ({self.mean.shape[0]}) != input dim ({self.dim})"
+        assert self.psi.shape[0] == self.dim, \
+            f"plda_psi dimension size ({self.psi.shape[0]}) != input dim ({self.dim})"
+        assert self.transformMat.shape[0] == self.dim, \
+            f"plda_transform_mat dimension size ({self.transformMat.shape[0]}) != input dim ({self.dim})"
+        assert self.transformMat.shape[0] == self.transformMat.shape[1], \
+            f"plda_transform_mat ({self.transformMat.shape[0]} x {self.transformMat.shape[1]}) is not a square matrix"
+
+    def build(self, input_shape):
+        if input_shape[-1] != self.dim:
+            raise ValueError(f"expected input vector dimension to be {self.dim}, got {input_shape[-1]}")
+        self.inputRank = len(input_shape)
+        if self.inputRank not in [2, 3]:
+            raise ValueError(f"expected input tensor rank to be 2 or 3, got {len(input_shape)}")
+        super().build(input_shape)
+
+    def get_config(self):
+        config = super().get_config()
+        config.update({"dim": self.dim, "normalize_length": self.normalizeLength,
+                       "simple_length_norm": self.simpleLengthNorm,
+                       "return_transformed": self.returnTransformed})
+        return config
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            N.require_cuda()
+            h = ctypes.c_void_p()
+            N.check(N.lib().ktf_plda_create(self.dim, T.host_ptr(self.mean), T.host_ptr(self.transformMat),
+                                            T.host_ptr(self.psi), int(self.normalizeLength),
+                                            int(self.simpleLengthNorm),
+                                            8 if self.paramDtype == np.float64 else 4, ctypes.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        try:
+            if self._handle:
+                N.lib().ktf_plda_destroy(self._handle)
+        except Exception:
+            pass
+
+    @property
+    def torchDtype(self):
+        return torch.float64 if self.paramDtype == np.float64 else torch.float32
+
+    def transformVector(self, x2d):
+        """(n, dim) float32 CUDA -> (n, dim) in the layer dtype: plda.py:184-196."""
+        n = x2d.shape[0]
+        u = torch.empty((n, self.dim), device=x2d.device, dtype=self.torchDtype)
+        N.check(N.lib().ktf_plda_transform(self.handle, T.ptr(x2d), n, T.ptr(u), T.stream_ptr()))
+        return u
+
+    def logLikelihoodRatio(self, u_test, u_enroll=None, out=None):
+        """scores[i, j] = LLR(test i | enrolled j): plda.py:215-245 (all-pairs)."""
+        u_enroll = u_test if u_enroll is None else u_enroll
+        nt, ne = u_test.shape[0], u_enroll.shape[0]
+        if out is None:
+            out = torch.empty((nt, ne), device=u_test.device, dtype=self.torchDtype)
+        N.check(N.lib().ktf_plda_score(self.handle, T.ptr(u_test), nt, T.ptr(u_enroll), ne, T.ptr(out),
+                                       out.stride(0), T.stream_ptr()))
+        return out
+
+    def call(self, inputs):
+        x = T.as_device(inputs)
+        self._maybe_build(x.shape)
+        if x.dim() == 3:
+            if x.shape[1] != 1:
+                raise ValueError(f"expected input of shape (batch, 1, dim), got {tuple(x.shape)}")
+            x = x[:, 0, :]
+        x = x.contiguous()
+        u = self.transformVector(x)
+        scores = self.logLikelihoodRatio(u)
+        if self.returnTransformed:
+            return T.like_input(scores, inputs), T.like_input(u[:, :, None], inputs)
+        return T.like_input(scores, inputs)

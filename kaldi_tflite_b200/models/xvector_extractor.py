@@ -1,0 +1,143 @@
+"""
+End-to-end wav -> x-vector model with the reference's surface
+(/root/reference/kaldi_tflite/lib/models/kaldi/xvector_extractor.py:25-186):
+`XvectorExtractorFromConfig(cfgPath, name)`, `XvectorExtractor(cfg, name, chunk_size)`.
+
+Differences that do not change results for the reference's use (batch 1):
+  * any batch is accepted: a (B, N) array, a 1-D (N,) array, or a list of 1-D arrays of
+    different lengths (ragged).  Utterances are independent (the reference collapses the batch
+    at tf.gather_nd, xvector_extractor.py:163-165, so it is batch-1 only).
+  * no network: when the Kaldi `final.raw` is absent the TDNN is randomly initialised with a
+    fixed seed and a warning is printed (the reference would download it, :55-65).
+"""
+
+import os
+import warnings
+
+import numpy as np
+import torch
+import yaml
+
+from .. import _native as N
+from .. import _tensor as T
+from ..io import ReadKaldiArray
+from ..layers import CMVN, MFCC, VAD, Framing
+from .sequential import SequentialFromConfig
+
+
+def _resolve(path, base_dirs):
+    if path is None or os.path.isabs(path) or os.path.exists(path):
+        return path
+    for b in base_dirs:
+        p = os.path.join(b, path)
+        if os.path.exists(p):
+            return p
+    return path
+
+
+def XvectorExtractorFromConfig(cfgPath: str, name: str = None, **kwargs):
+    with open(cfgPath) as f:
+        cfg = yaml.safe_load(f)
+    ext = cfg["extractor"]
+    # paths in the YAML are relative to the repository root (the reference runs from there)
+    bases = [os.getcwd(), os.path.dirname(os.path.abspath(cfgPath)),
+             os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(cfgPath)), "..", ".."))]
+    for key in ("model_config_path", "model_path", "global_mean_path", "lda_matrix_path"):
+        ext["xvec"][key] = _resolve(ext["xvec"].get(key), bases)
+    if not os.path.exists(ext["xvec"]["model_path"] or ""):
+        warnings.warn(f"Kaldi model '{ext['xvec']['model_path']}' not found and there is no network to "
+                      "download it: the TDNN is randomly initialised (seed 0)")
+    return XvectorExtractor(ext, name=name, **kwargs)
+
+
+class XvectorExtractor:
+
+    def __init__(self, cfg: dict, name: str = None, chunk_size: int = 300, precision: str = None,
+                 seed: int = 0, dither: float = None):
+        self.name = name
+        self.chunkSize = chunk_size
+        fr = dict(cfg["framing"])
+        mf = dict(cfg["mfcc"])
+        if dither is not None:
+            mf["dither"] = dither
+        self.framing = Framing(**fr)
+        self.mfcc = MFCC(**mf)
+        self.vad = VAD(**cfg["vad"])
+        self.cmvn = CMVN(**cfg["cmvn"])
+
+        with open(cfg["xvec"]["model_config_path"], "r") as f:
+            nnet3Cfg = yaml.safe_load(f)
+        model_path = cfg["xvec"].get("model_path")
+        if model_path is not None and not os.path.exists(model_path):
+            model_path = None
+        self.xvec = SequentialFromConfig(nnet3Cfg["model_config"], model_path, "cmvn2xvec",
+                                         precision=precision, seed=seed)
+
+        globalMean = ReadKaldiArray(cfg["xvec"]["global_mean_path"], binary=_is_binary(cfg["xvec"]["global_mean_path"]))
+        ldaMat = ReadKaldiArray(cfg["xvec"]["lda_matrix_path"], binary=_is_binary(cfg["xvec"]["lda_matrix_path"]))
+        self.xvecGlobalMean = np.ascontiguousarray(globalMean, dtype=np.float32)
+        self.ldaTransform = np.ascontiguousarray(ldaMat, dtype=np.float32)      # (lda_dim, dim + 1) = [L | o]
+        self.ldaOffset = self.ldaTransform[..., -1:].T                           # xvector_extractor.py:133
+        self.ldaMat = self.ldaTransform[..., :-1].T                              # :134
+        self._dev = None
+
+    # ---- stages, all on ragged (rows, dim) layouts ------------------------------------
+    def features(self, wav_flat, sample_offsets):
+        """Fused framing + MFCC over a ragged batch -> (rows, num_mfccs), frame offsets (CUDA int64)."""
+        fe = self.mfcc.frontend(self.framing.frameWidth, self.framing.frameShift)
+        if self.mfcc.windowing.dither != 0.0:
+            wav_flat = wav_flat + torch.randn_like(wav_flat) * float(self.mfcc.windowing.dither)
+        feats, fo = fe.forward_ragged(wav_flat, sample_offsets)
+        return feats, torch.from_numpy(fo).to(wav_flat.device)
+
+    def embed(self, feats, offsets, max_frames=None):
+        mask = self.vad.mask_ragged(feats, offsets)
+        voiced, voffs, _ = self.vad.compact_ragged(feats, mask, offsets, gather=True)
+        if bool((voffs[1:] == voffs[:-1]).any().item()):
+            raise ValueError("an utterance has no voiced frames after VAD")
+        normed, _ = self.cmvn.forward_ragged(voiced, voffs, max_frames=max_frames)
+        emb, _ = self.xvec.forward_ragged(normed, voffs)
+        return emb, mask, voffs
+
+    def backend(self, emb):
+        if self._dev is None:
+            self._dev = (T.as_device(self.xvecGlobalMean), T.as_device(self.ldaTransform))
+        mean, tr = self._dev
+        B, D = emb.shape
+        out_dim = tr.shape[0]
+        y = torch.empty((B, out_dim), device=emb.device, dtype=torch.float32)
+        N.check(N.lib().ktf_lda_forward(T.ptr(emb), B, D, out_dim, T.ptr(mean), T.ptr(tr), 1, T.ptr(y),
+                                        T.stream_ptr()))
+        return y
+
+    def _flatten(self, inputs):
+        if isinstance(inputs, (list, tuple)):
+            arrs = [T.as_device(a).reshape(-1) for a in inputs]
+            lens = [int(a.numel()) for a in arrs]
+            return torch.cat(arrs), np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        x = T.as_device(inputs)
+        if x.dim() == 1:
+            x = x[None]
+        if x.dim() != 2:
+            raise ValueError(f"expected input of shape (batch, samples), got {tuple(x.shape)}")
+        B, n = x.shape
+        return x.reshape(-1), (np.arange(B + 1, dtype=np.int64) * n)
+
+    def __call__(self, inputs, training: bool = False, return_intermediate: bool = False):
+        wav_flat, so = self._flatten(inputs)
+        feats, offsets = self.features(wav_flat, so)
+        emb, mask, voffs = self.embed(feats, offsets, max_frames=self.framing.numFrames(int(np.max(np.diff(so)))))
+        y = self.backend(emb)
+        ref = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
+        out = T.like_input(y.squeeze(), ref)                      # tf.squeeze (:184)
+        if return_intermediate:
+            return out, {"mfcc": feats, "frame_offsets": offsets, "mask": mask,
+                         "voiced_offsets": voffs, "embedding": emb}
+        return out
+
+    call = __call__
+
+
+def _is_binary(path):
+    with open(path, "rb") as f:
+        return f.read(2) == b"\x00B"

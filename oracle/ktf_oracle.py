@@ -93,16 +93,20 @@ def window_function(window_type, M, blackman_coeff=0.42):
 
 def log_energy(x, energy_floor=0.0, epsilon=1e-7):
     """windowing.py:174-178 -- clip(log(relu(sum x^2) + eps), floor, max)."""
-    e = np.sum(x * x, axis=-1, keepdims=True, dtype=F32)
-    e = np.log(np.maximum(e, F32(0)) + F32(epsilon)).astype(F32)
-    return np.clip(e, F32(energy_floor), np.finfo(F32).max).astype(F32)
+    dt = x.dtype.type
+    e = np.sum(x * x, axis=-1, keepdims=True, dtype=dt)
+    e = np.log(np.maximum(e, dt(0)) + dt(np.float32(epsilon))).astype(dt)
+    return np.clip(e, dt(energy_floor), np.finfo(F32).max).astype(dt)
 
 
 def windowing(frames, window_type="povey", blackman_coeff=0.42, dither=0.0,
               remove_dc_offset=True, preemphasis_coefficient=0.97,
               return_energy=True, raw_energy=True, energy_floor=0.0, epsilon=1e-7,
-              rng=None):
-    """windowing.py:180-209."""
+              rng=None, precise=False):
+    """windowing.py:180-209.  `precise=True` evaluates the same formulas in float64 (the
+    constant tables stay the float32 ones the reference stores): the yardstick that tells
+    float32 rounding noise apart from real differences."""
+    F32 = np.float64 if precise else np.float32
     x = np.asarray(frames, dtype=F32)
     if dither != 0.0:
         rng = rng or np.random.default_rng()
@@ -113,11 +117,11 @@ def windowing(frames, window_type="povey", blackman_coeff=0.42, dither=0.0,
     if return_energy and raw_energy:
         energy = log_energy(x, energy_floor, epsilon)
     if preemphasis_coefficient > 0:
-        c = F32(preemphasis_coefficient)
+        c = F32(np.float32(preemphasis_coefficient))      # TF rounds the python scalar to float32
         first = x[..., :1] - c * x[..., :1]
         rest = x[..., 1:] - c * x[..., :-1]
         x = np.concatenate([first, rest], axis=-1)
-    x = x * window_function(window_type, x.shape[-1], blackman_coeff)
+    x = x * window_function(window_type, x.shape[-1], blackman_coeff).astype(F32)
     if return_energy:
         if not raw_energy:
             energy = log_energy(x, energy_floor, epsilon)
@@ -183,8 +187,10 @@ def mel_bank(window_size, num_bins=23, sample_frequency=16000.0,
 
 
 def filterbank(frames, num_bins=23, sample_frequency=16000.0, high_freq_cutoff=0.0,
-               low_freq_cutoff=20.0, use_log_fbank=True, use_power=True, epsilon=1e-7):
+               low_freq_cutoff=20.0, use_log_fbank=True, use_power=True, epsilon=1e-7,
+               precise=False):
     """filterbank.py:225-242 -- pad -> rfft -> abs -> pow2 -> @melBank -> log(relu+eps)."""
+    F32 = np.float64 if precise else np.float32
     x = np.asarray(frames, dtype=F32)
     fft_length, bank = mel_bank(x.shape[-1], num_bins, sample_frequency,
                                 high_freq_cutoff, low_freq_cutoff)
@@ -192,9 +198,9 @@ def filterbank(frames, num_bins=23, sample_frequency=16000.0, high_freq_cutoff=0
     spec = np.abs(spec).astype(F32)
     if use_power:
         spec = spec * spec
-    feats = np.matmul(spec, bank).astype(F32)
+    feats = np.matmul(spec, bank.astype(F32)).astype(F32)
     if use_log_fbank:
-        feats = np.log(np.maximum(feats, F32(0)) + F32(epsilon)).astype(F32)
+        feats = np.log(np.maximum(feats, F32(0)) + F32(np.float32(epsilon))).astype(F32)
     return feats
 
 
@@ -230,23 +236,25 @@ def mfcc(frames, num_mfccs=23, num_mels=23, cepstral_lifter=22, use_energy=True,
          sample_frequency=16000.0, high_freq_cutoff=0.0, low_freq_cutoff=20.0,
          use_log_fbank=True, use_power=True, window_type="povey", dither=0.0,
          remove_dc_offset=True, preemphasis_coefficient=0.97, raw_energy=True,
-         energy_floor=0.0, epsilon=1e-7):
+         energy_floor=0.0, epsilon=1e-7, precise=False):
     """mfcc.py:197-244 -- windowing -> filterbank -> DCT -> lifter -> C0 <- log-energy."""
     if num_mfccs > num_mels:
         raise ValueError("num_mfccs must be <= num_mels")
+    F32 = np.float64 if precise else np.float32
     w = windowing(frames, window_type=window_type, dither=dither,
                   remove_dc_offset=remove_dc_offset,
                   preemphasis_coefficient=preemphasis_coefficient,
                   return_energy=use_energy, raw_energy=raw_energy,
-                  energy_floor=energy_floor, epsilon=epsilon)
+                  energy_floor=energy_floor, epsilon=epsilon, precise=precise)
     if use_energy:
         w, energy = w
     fb = filterbank(w, num_bins=num_mels, sample_frequency=sample_frequency,
                     high_freq_cutoff=high_freq_cutoff, low_freq_cutoff=low_freq_cutoff,
-                    use_log_fbank=use_log_fbank, use_power=use_power, epsilon=epsilon)
-    out = np.matmul(fb, dct_matrix(num_mels, num_mfccs)).astype(F32)
+                    use_log_fbank=use_log_fbank, use_power=use_power, epsilon=epsilon,
+                    precise=precise)
+    out = np.matmul(fb, dct_matrix(num_mels, num_mfccs).astype(F32)).astype(F32)
     if cepstral_lifter > 1 and num_mfccs > 1:
-        out = out * lifter_coeffs(num_mfccs, cepstral_lifter)
+        out = out * lifter_coeffs(num_mfccs, cepstral_lifter).astype(F32)
     if use_energy:
         out = out.copy()
         out[..., 0] = energy[..., 0]

@@ -163,7 +163,7 @@ def main():
         "single_cfg": json.dumps(single.cfg),
         "single_in": single.inputs, "single_out": single.outputs,
         "narrow_in": narrow.inputs, "narrow_out": narrow.outputs,
-        "narrow_config": narrow.config,
+        "narrow_config": json.dumps(list(narrow.config)),
         "narrow_components": json.dumps([
             {k: (v if isinstance(v, (str, int, float, bool)) else None) for k, v in c.items()}
             for c in narrow.components]),
