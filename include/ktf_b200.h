@@ -195,6 +195,23 @@ int ktf_affine_forward(const ktf_affine* a, const float* x_dev, const int64_t* i
                        const int64_t* out_offsets_dev, int64_t batch, int64_t total_in_rows,
                        int64_t total_out_rows, float* y_dev, float* stats_dev, void* stream);
 
+/* Whole network on the tcgen05 engine: [affine(+ReLU+BN)] x n1 -> StatsPooling(reduce-all,
+ * stats_pooling.py:211-240) -> [affine(+ReLU+BN)] x n2, i.e. the keras Sequential built by
+ * models/kaldi/sequential.py:86-143.  All layers must have been created with KTF_PREC_BF16,
+ * padding SAME and subsampling 1.  Activations stay on the device in bf16 between layers (fp32
+ * accumulation in TMEM); the splice of every layer is implicit (shifted TMA loads).
+ * stats_after_layer = index of the layer whose output is pooled over time (-1: no pooling);
+ * layers after it must have context [0].  The stack borrows the layer handles. */
+typedef struct ktf_tdnn_stack ktf_tdnn_stack;
+int ktf_tdnn_stack_create(ktf_affine* const* layers, int32_t num_layers, int32_t stats_after_layer,
+                          int32_t include_std, float stats_epsilon, ktf_tdnn_stack** out);
+void ktf_tdnn_stack_destroy(ktf_tdnn_stack* s);
+int32_t ktf_tdnn_stack_out_dim(const ktf_tdnn_stack* s);
+/* feats_dev (total_rows, D0) fp32, utterance b = rows offsets_dev[b]..[b+1) (device int64, batch+1).
+ * out_dev: (batch, out_dim) fp32 when the stack pools over time, else (total_rows, out_dim). */
+int ktf_tdnn_stack_forward(const ktf_tdnn_stack* s, const float* feats_dev, const int64_t* offsets_dev,
+                           int64_t batch, int64_t total_rows, float* out_dev, void* stream);
+
 /* Element-wise helpers for callers that use ReLU / BatchNorm as stand-alone layers. */
 int ktf_relu_forward(const float* x_dev, int64_t n, float* y_dev, void* stream);
 int ktf_scale_offset_forward(const float* x_dev, int64_t rows, int32_t dim,

@@ -197,6 +197,16 @@ inline unsigned grid_for(long long n, int threads) {
 
 }  // namespace
 
+namespace ktf {
+int stats_sums_f32(const float* y_dev, const int64_t* offsets_dev, int64_t batch, int dim, float* sums_dev,
+                   cudaStream_t st) {
+  dim3 g((unsigned)batch, (unsigned)((dim + 127) / 128));
+  stats_sum_kernel<<<g, 128, 0, st>>>(y_dev, (const long long*)offsets_dev, dim, 1, sums_dev);
+  KTF_LAUNCH_OK();
+  return KTF_OK;
+}
+}  // namespace ktf
+
 extern "C" {
 
 int ktf_affine_create(const ktf_affine_cfg* cfg, const float* weights_host, const float* bias_host,

@@ -18,4 +18,7 @@ void affine_tc_release(ktf_affine* a);
 int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in_offsets_dev,
                       const int64_t* out_offsets_dev, int64_t batch, int64_t total_in_rows,
                       int64_t total_out_rows, float* y_dev, float* stats_dev, cudaStream_t st);
+// per-utterance column sums / sums of squares of an fp32 (rows, dim) matrix -> (batch, 2, dim)
+int stats_sums_f32(const float* y_dev, const int64_t* offsets_dev, int64_t batch, int dim, float* sums_dev,
+                   cudaStream_t st);
 }  // namespace ktf

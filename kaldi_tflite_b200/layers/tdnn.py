@@ -101,6 +101,35 @@ class _Affine:
         return y.reshape(B, To, self.out_dim)
 
 
+class _Stack:
+    """Owns one ktf_tdnn_stack: the whole affine/ReLU/BN (+ reduce-all stats) network on the tcgen05 engine."""
+
+    def __init__(self, affines, stats_after=-1, include_std=True, epsilon=1e-10):
+        N.require_cuda()
+        self.affines = list(affines)                 # keep the borrowed handles alive
+        arr = (ctypes.c_void_p * len(affines))(*[a.handle for a in affines])
+        self.handle = ctypes.c_void_p()
+        N.check(N.lib().ktf_tdnn_stack_create(arr, len(affines), stats_after, int(include_std),
+                                              float(epsilon), ctypes.byref(self.handle)))
+        self.out_dim = int(N.lib().ktf_tdnn_stack_out_dim(self.handle))
+        self.pools = stats_after >= 0
+
+    def __del__(self):
+        try:
+            if self.handle:
+                N.lib().ktf_tdnn_stack_destroy(self.handle)
+        except Exception:
+            pass
+
+    def forward_ragged(self, x2d, offsets):
+        rows, _ = x2d.shape
+        B = offsets.numel() - 1
+        out = torch.empty((B if self.pools else rows, self.out_dim), device=x2d.device, dtype=torch.float32)
+        N.check(N.lib().ktf_tdnn_stack_forward(self.handle, T.ptr(x2d), T.ptr(offsets), B, rows, T.ptr(out),
+                                               T.stream_ptr()))
+        return out
+
+
 def glorot_uniform(shape, rng):
     """keras GlorotUniform: U(-l, l), l = sqrt(6 / (fan_in + fan_out)) (tdnn.py:50-51)."""
     if len(shape) == 1:

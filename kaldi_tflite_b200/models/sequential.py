@@ -57,6 +57,7 @@ class Sequential:
         self.precision = precision
         self.dtype = "float32"
         self._plan = None
+        self._stack = None
         if input_shape is not None and input_shape[-1] is not None:
             self._build_layers(input_shape[-1])
 
@@ -79,6 +80,29 @@ class Sequential:
     def invalidate(self):
         """Drop the fused plan (call after changing any layer's weights)."""
         self._plan = None
+
+    def _resolved_precision(self):
+        from ..layers import tdnn as _t
+        return (self.precision or _t.DEFAULT_PRECISION).lower()
+
+    def _try_stack(self, plan):
+        """bf16: run the whole [affine]* -> stats(reduce) -> [affine]* network as ONE tcgen05 stack."""
+        from ..layers.tdnn import _Stack
+        affines, stats_after, stats = [], -1, None
+        for kind, obj, st in plan:
+            if kind != "affine" or not obj.same:
+                return None
+            affines.append(obj)
+            if st is not None:
+                if stats is not None:
+                    return None
+                stats, stats_after = st, len(affines) - 1
+        if stats_after >= 0:
+            for a in affines[stats_after + 1:]:
+                if a.context != [0]:
+                    return None
+        return _Stack(affines, stats_after, stats.includeStd if stats else True,
+                      stats.epsilon if stats else 1e-10)
 
     def _make_plan(self):
         plan, i, L = [], 0, self.layers
@@ -112,7 +136,13 @@ class Sequential:
         if self._plan is None:
             self._build_layers(x2d.shape[-1])
             self._plan = self._make_plan()
+            self._stack = None
+            if self._resolved_precision() in ("bf16", "bfloat16"):
+                self._stack = self._try_stack(self._plan)
         B = offsets.numel() - 1
+        if self._stack is not None:
+            y = self._stack.forward_ragged(x2d, offsets)
+            return y, (T.uniform_offsets(B, 1) if self._stack.pools else offsets)
         for kind, obj, stats in self._plan:
             if kind == "affine":
                 if stats is not None:

@@ -209,6 +209,61 @@ def test_sitw_stack_fp32_vs_oracle(ktf):
     assert np.max(np.abs(got - want)) < 1e-3
 
 
+def _bf16_round(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("D,U,ctx", [(512, 512, [-2, 0, 2]), (512, 1500, [0]), (30, 512, [-2, -1, 0, 1, 2]),
+                                     (64, 40, [-3, 0, 3]), (3000, 512, [0])])
+def test_tc_layer_vs_exact_bf16_product(ktf, D, U, ctx):
+    # tcgen05 engine, single layer: compare with an fp32 evaluation of the SAME bf16-rounded operands
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((3, 157, D)).astype(np.float32)
+    l = ktf.layers.TDNN(U, context=ctx, precision="bf16", seed=3)
+    got = l(x)
+    kernel, bias = l.get_weights()
+    want = O.tdnn(_bf16_round(x), _bf16_round(kernel), bias, ctx)
+    assert got.shape == want.shape
+    err = np.max(np.abs(got - want))
+    assert err < 2e-3 * max(1.0, float(np.max(np.abs(want)))), err
+    # and it is close to the full-precision layer (bf16 operand rounding only)
+    full = O.tdnn(x, kernel, bias, ctx)
+    assert np.max(np.abs(got - full)) < 0.05 * max(1.0, float(np.max(np.abs(full))))
+
+
+def test_sitw_stack_bf16_vs_oracle(ktf):
+    # north star: x-vector cosine >= 0.9999 at bf16 TDNN precision (operands bf16, fp32 accumulation in
+    # TMEM, bf16 inter-layer activations), full SITW widths, seeded random weights
+    g = load_golden("tdnn.npz")
+    base = g["sitw_chunk_mfcc"][0].astype(np.float32)
+    x = [base, base[::-1].copy(), base[:97].copy(), np.concatenate([base, base[::2]])]
+    mdl = sitw_model(ktf, precision="bf16")
+    layers = sitw_layers_for_oracle(mdl)
+    for xi in x:
+        got = mdl(xi[None])
+        want = O.sequential(xi[None], layers)
+        assert got.shape == want.shape == (1, 1, 512)
+        assert cosine(got, want) >= 0.9999, cosine(got, want)
+    # ragged batch through the stack equals the per-utterance runs
+    import torch
+    flat = torch.from_numpy(np.concatenate(x)).cuda()
+    offs = torch.tensor(np.concatenate([[0], np.cumsum([len(v) for v in x])]), dtype=torch.int64, device="cuda")
+    y, _ = mdl.forward_ragged(flat, offs)
+    y = y.cpu().numpy()
+    for b, xi in enumerate(x):
+        assert cosine(y[b], mdl(xi[None])) > 0.99999
+
+
+def test_xvector_extractor_bf16_vs_oracle(ktf):
+    wav = read_wav_int16(golden_path("librispeech_2.wav"))
+    cfg = extractor_cfg()
+    ext = ktf.models.XvectorExtractor(cfg, precision="bf16", seed=0)
+    got = ext(wav)
+    want = O.xvector_extractor(wav, cfg, sitw_layers_for_oracle(ext.xvec), ext.xvecGlobalMean, ext.ldaTransform)
+    assert cosine(got, want) >= 0.9999, cosine(got, want)
+
+
 def extractor_cfg():
     import os, yaml
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
