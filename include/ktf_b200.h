@@ -201,7 +201,10 @@ int ktf_affine_forward(const ktf_affine* a, const float* x_dev, const int64_t* i
  * padding SAME and subsampling 1.  Activations stay on the device in bf16 between layers (fp32
  * accumulation in TMEM); the splice of every layer is implicit (shifted TMA loads).
  * stats_after_layer = index of the layer whose output is pooled over time (-1: no pooling);
- * layers after it must have context [0].  The stack borrows the layer handles. */
+ * layers after it must have context [0].  The pooled layer runs with its operands swapped and
+ * accumulates the per-utterance sum / sum of squares in its epilogue (fp32), so its activation is
+ * never stored.  The stack borrows the layer handles and owns a grow-only device workspace:
+ * forward calls on ONE stack handle must be issued on one stream at a time. */
 typedef struct ktf_tdnn_stack ktf_tdnn_stack;
 int ktf_tdnn_stack_create(ktf_affine* const* layers, int32_t num_layers, int32_t stats_after_layer,
                           int32_t include_std, float stats_epsilon, ktf_tdnn_stack** out);
@@ -209,7 +212,7 @@ void ktf_tdnn_stack_destroy(ktf_tdnn_stack* s);
 int32_t ktf_tdnn_stack_out_dim(const ktf_tdnn_stack* s);
 /* feats_dev (total_rows, D0) fp32, utterance b = rows offsets_dev[b]..[b+1) (device int64, batch+1).
  * out_dev: (batch, out_dim) fp32 when the stack pools over time, else (total_rows, out_dim). */
-int ktf_tdnn_stack_forward(const ktf_tdnn_stack* s, const float* feats_dev, const int64_t* offsets_dev,
+int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int64_t* offsets_dev,
                            int64_t batch, int64_t total_rows, float* out_dev, void* stream);
 
 /* Element-wise helpers for callers that use ReLU / BatchNorm as stand-alone layers. */

@@ -54,6 +54,67 @@ inline int num_sms() {
   return n;
 }
 
+// Stream-ordered scratch allocation.  The device's default memory pool is told to keep freed
+// blocks (release threshold = max) on first use: with the driver default (0) every stream / event
+// synchronisation hands the pool's memory back to the OS and the next call pays to map it again.
+inline cudaError_t malloc_async(void** p, size_t bytes, cudaStream_t st) {
+  static int pooled_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (pooled_dev != dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pooled_dev = dev;
+  }
+  return cudaMallocAsync(p, bytes, st);
+}
+
+// Grow-only device workspace owned by a handle (handles own packed weights, tables and a
+// workspace).  Growth is a cudaFree + cudaMalloc (device-synchronising); steady state is free.
+struct Workspace {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return KTF_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      e = cudaMalloc(&ptr, bytes);
+      if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("cudaMalloc(%zu) for a workspace failed: %s", bytes, cudaGetErrorString(e));
+        return KTF_ENOMEM;
+      }
+      cap = bytes;
+      return KTF_OK;
+    }
+    cap = want;
+    return KTF_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+// Carves 256-byte aligned regions out of a workspace (sizes first, pointers after ensure()).
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return at;
+  }
+};
+
 template <typename T>
 inline int upload(T** dst, const T* src, size_t n) {
   cudaError_t e = cudaMalloc((void**)dst, n * sizeof(T));

@@ -801,7 +801,7 @@ int ktf_frontend_forward_ragged(const ktf_frontend* fe, const float* wav_dev, in
   for (int64_t b = 0; b <= batch; ++b) frame_offsets_host[b] = fo[b];
 
   long long* dev = nullptr;
-  KTF_CUDA(cudaMallocAsync((void**)&dev, host.size() * sizeof(long long), st));
+  KTF_CUDA(ktf::malloc_async((void**)&dev, host.size() * sizeof(long long), st));
   KTF_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
   KTF_CUDA(cudaStreamSynchronize(st));  // `host` is pageable and dies at return
 

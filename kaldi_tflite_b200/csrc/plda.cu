@@ -8,12 +8,23 @@
 //     A_i = sum_d u_i[d]^2 * (0.5/v0 - 0.5/v1) - 0.5 * (sum log v1 - sum log v0)
 //     B_j = -0.5 * sum_d (r u_j[d])^2 / v1
 // Arithmetic is fp32 or fp64 (the reference's default parameter dtype) per handle.
+//
+// fp32 handles run the cross term on the tcgen05 engine (tdnn_tc.cu) at fp32-equivalent precision:
+// both operands are split into fp16 hi + lo parts (22 significant bits) and the three significant
+// partial products are evaluated as ONE GEMM over a tripled K:
+//     [a_hi | a_lo | a_hi] . [b_hi | b_hi | b_lo]^T = a_hi b_hi + a_lo b_hi + a_hi b_lo      (fp32 accumulate)
+// with A_i / B_j added in the epilogue.  At dim 128 the kernel is bound by the fp32 score writes
+// (64 FLOP per output byte), not by the tensor pipe.  fp64 handles and
+// configurations whose operands could leave the fp16 range use exact SIMT tiles.
+#include <cuda_fp16.h>
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "tdnn_internal.cuh"
 
 struct ktf_plda {
   int dim = 0;
@@ -27,6 +38,8 @@ struct ktf_plda {
   void* d_wa = nullptr;      // (dim)  0.5/v0 - 0.5/v1
   void* d_wb = nullptr;      // (dim)  -0.5 r^2 / v1
   double logdet_term = 0.0;  // -0.5 (sum log v1 - sum log v0)
+  int use_tc = 0;            // fp32 handle on an sm_100 device with fp16-safe operand range
+  mutable ktf::Workspace ws; // split operands + A_i / B_j of the tensor-core path (grow-only)
 };
 
 namespace {
@@ -105,6 +118,57 @@ __global__ void plda_quad_kernel(const T* __restrict__ u, long long n, int dim, 
   if (lane == 0) out[row] = acc + add;
 }
 
+// fp32 rows (optionally scaled per column) -> fp16 hi/lo split rows of 3*dim columns:
+//   layout 0 (test side):   [hi | lo | hi]      layout 1 (enrolled side): [hi | hi | lo]
+__global__ void plda_split_kernel(const float* __restrict__ u, long long n, int dim, const float* __restrict__ c,
+                                  int layout, __half* __restrict__ out) {
+  const long long total = n * dim;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / dim;
+    const int d = (int)(i - r * dim);
+    float v = u[i];
+    if (c) v *= c[d];
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    __half* o = out + r * (3LL * dim);
+    o[d] = hi;
+    o[dim + d] = layout == 0 ? lo : hi;
+    o[2 * dim + d] = layout == 0 ? hi : lo;
+  }
+}
+
+int score_tc(const ktf_plda* p, const float* ut, int64_t nt, const float* ue, int64_t ne, float* scores, int64_t ld,
+             cudaStream_t st) {
+  const int dim = p->dim;
+  const long long K = 3LL * dim;
+  ktf::Carver cv;
+  const size_t o_a = cv.take((size_t)nt * K * sizeof(__half));
+  const size_t o_b = cv.take((size_t)ne * K * sizeof(__half));
+  const size_t o_ai = cv.take((size_t)nt * sizeof(float));
+  const size_t o_bj = cv.take((size_t)ne * sizeof(float));
+  int rc = p->ws.ensure(cv.off);
+  if (rc != KTF_OK) return rc;
+  char* base = static_cast<char*>(p->ws.ptr);
+  __half* As = reinterpret_cast<__half*>(base + o_a);
+  __half* Bs = reinterpret_cast<__half*>(base + o_b);
+  float* Ai = reinterpret_cast<float*>(base + o_ai);
+  float* Bj = reinterpret_cast<float*>(base + o_bj);
+  plda_quad_kernel<float><<<(unsigned)((nt + 7) / 8), 256, 0, st>>>(ut, nt, dim, (const float*)p->d_wa,
+                                                                    (float)p->logdet_term, Ai);
+  KTF_LAUNCH_OK();
+  plda_quad_kernel<float><<<(unsigned)((ne + 7) / 8), 256, 0, st>>>(ue, ne, dim, (const float*)p->d_wb, 0.0f, Bj);
+  KTF_LAUNCH_OK();
+  auto blocks = [](long long items) {
+    return (unsigned)std::min<long long>((items + 255) / 256, (long long)ktf::num_sms() * 16);
+  };
+  plda_split_kernel<<<blocks(nt * dim), 256, 0, st>>>(ut, nt, dim, (const float*)p->d_c, 0, As);
+  KTF_LAUNCH_OK();
+  plda_split_kernel<<<blocks(ne * dim), 256, 0, st>>>(ue, ne, dim, nullptr, 1, Bs);
+  KTF_LAUNCH_OK();
+  return ktf::tc_gemm_nt(As, nt, K, Bs, ne, K, K, /*fp16=*/1, Ai, Bj, scores, ld, st);
+}
+
 template <typename T>
 int upload_as(void** dst, const std::vector<double>& v) {
   std::vector<T> tmp(v.size());
@@ -134,7 +198,7 @@ int score_impl(const ktf_plda* p, const T* ut, int64_t nt, const T* ue, int64_t 
                cudaStream_t st) {
   const int dim = p->dim;
   T* ab = nullptr;
-  KTF_CUDA(cudaMallocAsync((void**)&ab, (size_t)(nt + ne) * sizeof(T), st));
+  KTF_CUDA(ktf::malloc_async((void**)&ab, (size_t)(nt + ne) * sizeof(T), st));
   T* A = ab;
   T* B = ab + nt;
   plda_quad_kernel<T><<<(unsigned)((nt + 7) / 8), 256, 0, st>>>(ut, nt, dim, (const T*)p->d_wa,
@@ -198,12 +262,20 @@ int ktf_plda_create(int32_t dim, const double* mean_host, const double* transfor
   UP(d_wa, wa);
   UP(d_wb, wb);
 #undef UP
+  // tensor-core path: fp32 handle, sm_100 device, K = 3*dim a multiple of 8, and operands that stay far
+  // inside the fp16 range: after length normalisation |u_d| <= sqrt(dim * (psi_d + 1)).
+  if (f32 && dim % 8 == 0 && normalize_length && ktf_device_arch() >= 100) {
+    double bound = 0.0;
+    for (int r = 0; r < dim; ++r) bound = std::max(bound, sqrt((double)dim * (psi[r] + 1.0)));
+    p->use_tc = bound < 3.0e4;
+  }
   *out = p;
   return KTF_OK;
 }
 
 void ktf_plda_destroy(ktf_plda* p) {
   if (!p) return;
+  p->ws.release();
   cudaFree(p->d_T);
   cudaFree(p->d_offset);
   cudaFree(p->d_psi);
@@ -227,6 +299,9 @@ int ktf_plda_score(const ktf_plda* p, const void* u_test_dev, int64_t n_test, co
   KTF_CHECK_ARG(ld >= n_enroll, "ld must be >= n_enroll");
   if (n_test <= 0 || n_enroll <= 0) return KTF_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->use_tc)
+    return score_tc(p, (const float*)u_test_dev, n_test, (const float*)u_enroll_dev, n_enroll, (float*)scores_dev, ld,
+                    st);
   return p->dtype_bytes == 4
              ? score_impl<float>(p, (const float*)u_test_dev, n_test, (const float*)u_enroll_dev, n_enroll,
                                  (float*)scores_dev, ld, st)

@@ -277,7 +277,7 @@ int ktf_affine_forward(const ktf_affine* a, const float* x_dev, const int64_t* i
 
   const int K = c.num_context * c.in_dim, U = c.out_dim;
   RowInfo* info = nullptr;
-  KTF_CUDA(cudaMallocAsync((void**)&info, total_out_rows * sizeof(RowInfo), st));
+  KTF_CUDA(ktf::malloc_async((void**)&info, total_out_rows * sizeof(RowInfo), st));
   const int start = (c.padding_valid && c.context[0] < 0) ? -c.context[0] : 0;
   row_info_kernel<<<grid_for(total_out_rows, 256), 256, 0, st>>>(
       (const long long*)in_offsets_dev, (const long long*)out_offsets_dev, batch, total_out_rows, start,
@@ -285,7 +285,7 @@ int ktf_affine_forward(const ktf_affine* a, const float* x_dev, const int64_t* i
   KTF_LAUNCH_OK();
 
   float* y = y_dev;
-  if (y == nullptr) KTF_CUDA(cudaMallocAsync((void**)&y, (size_t)total_out_rows * U * sizeof(float), st));
+  if (y == nullptr) KTF_CUDA(ktf::malloc_async((void**)&y, (size_t)total_out_rows * U * sizeof(float), st));
 
   SpliceLoad al;
   al.x = x_dev;
@@ -349,7 +349,7 @@ int ktf_stats_reduce(const float* x_dev, const int64_t* offsets_dev, int64_t bat
   if (batch <= 0) return KTF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   float* sums = nullptr;
-  KTF_CUDA(cudaMallocAsync((void**)&sums, (size_t)batch * 2 * dim * sizeof(float), st));
+  KTF_CUDA(ktf::malloc_async((void**)&sums, (size_t)batch * 2 * dim * sizeof(float), st));
   dim3 g((unsigned)batch, (unsigned)((dim + 127) / 128));
   stats_sum_kernel<<<g, 128, 0, st>>>(x_dev, (const long long*)offsets_dev, dim, input_period, sums);
   KTF_LAUNCH_OK();

@@ -1,24 +1,32 @@
-// tcgen05 / TMEM implicit-GEMM engine for the TDNN stack (sm_100a only).
+// tcgen05 / TMEM implicit-GEMM engine for the TDNN stack and PLDA scoring (sm_100a only).
 //
-// Replaces the tf.gather + tf.nn.conv2d formulation of layers/tdnn/tdnn.py:251-280 and the keras
+// Replaces the tf.gather + tf.nn.conv2d formulation of layers/tdnn/tdnn.py:251-280, the keras
 // ReLU / BatchNormalization passes that follow it (models/kaldi/sequential.py:71-76,
-// layers/normalization/batchnorm.py:81-88) with ONE warp-specialised kernel per layer:
+// layers/normalization/batchnorm.py:81-88) and the reduce-all branch of
+// layers/stats/stats_pooling.py:211-240 with ONE warp-specialised kernel per layer:
 //
 //   y[r, u] = scale[u] * relu( sum_k sum_d x[r + ctx_k, d] * W[u, k*D + d] + bias[u] ) + offset[u]
 //
-//   * operands bf16, accumulation fp32 in TMEM (tcgen05.mma.cta_group::1.kind::f16, M128 x N256 x K16);
+//   * operands 16-bit (bf16 for the TDNN, fp16 hi/lo splits for PLDA), accumulation fp32 in TMEM
+//     (tcgen05.mma.cta_group::1.kind::f16, M128 x N256 x K16);
 //   * the frame splice is IMPLICIT: tap k is a TMA box load of the activation matrix shifted by ctx_k
 //     rows -- the (B, T, K, D) gathered tensor of the reference is never built;
 //   * edge clamping (tdnn.py:244-247) is provided by the activation layout: every utterance carries
 //     kHalo replicated rows on both sides ("padded rows"); the epilogue of each layer writes the halo
 //     replicas the next layer's taps need and skips the halo rows of its own tile;
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
-//     warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/BN -> bf16/fp32 -> global);
+//     warps 2..9 = epilogue (two warps per TMEM lane quarter, each owning half of the tile's columns;
+//     TMEM loads are software-pipelined against the bias/ReLU/BN math and the global stores);
 //   * 4-stage smem ring (48 KB per stage) between TMA and MMA, 2 accumulator stages of 256 TMEM columns
-//     between MMA and epilogue, persistent CTAs (one per SM) walking output tiles n-fastest so that the
-//     n-tiles of one row block run concurrently and share the activation rows through L2.
+//     between MMA and epilogue, persistent CTAs (one per SM);
+//   * three epilogues: bf16 rows (next layer's operand), fp32 rows (+ per-row / per-column addends:
+//     PLDA's A_i + B_j), and STATS: the layer that feeds StatsPooling runs with the operands swapped
+//     (M = units, N = frames), so a thread owns ONE unit and walks the frames of the tile in its own
+//     registers -- per-utterance sum / sum-of-squares need no cross-thread reduction and the widest
+//     activation of the network (frames x 1500) is never written to HBM.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <vector>
@@ -32,12 +40,17 @@ constexpr int kHalo = 4;          // replicated rows on each side of every utter
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;
-constexpr int kThreadsTc = 192;   // 6 warps
-constexpr int kABytes = BM * BK * 2;   // 16 KB
-constexpr int kBBytes = BN * BK * 2;   // 32 KB
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;          // 256
+constexpr int kThreadsTc = 64 + kEpiThreads;         // 10 warps
+constexpr int kABytes = BM * BK * 2;                 // 16 KB
+constexpr int kBBytes = BN * BK * 2;                 // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kSmemTc = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
-                        kAccStages * 3 * BN * 4 /*epilogue vectors*/;
+constexpr int kVecBytes = kAccStages * 3 * BN * 4;   // epilogue vectors (bias / scale / offset)
+constexpr int kSegBytes = kAccStages * BN * 4;       // STATS: utterance id of every frame of the tile
+constexpr int kSmemTc = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kVecBytes + kSegBytes;
+
+enum { kModeBf16 = 0, kModeF32 = 1, kModeStats = 2 };
 
 // rowmap flags
 constexpr int kRowStore = 1, kRowFirst = 2, kRowLast = 4;
@@ -47,15 +60,20 @@ struct TcArgs {
   int ctx[KTF_MAX_CONTEXT];
   int kblocks_per_tap;      // ceil(D / 64)
   int tap_cols;             // column distance between taps in the weight matrix (= D)
-  long long m_rows;         // rows of the A / output matrices (padded rows)
-  int n_cols;               // U
+  int shift_b;              // 0: taps shift the A rows (activations are A); 1: taps shift the B rows (STATS)
+  int fp16;                 // operand format: 0 = bf16, 1 = fp16
+  long long m_rows;         // rows of the A operand (output rows; STATS: units)
+  long long n_rows;         // rows of the B operand (output columns; STATS: frames)
   const int* rowmap;        // per output row flags, or nullptr = store every row < m_rows
-  const float* bias;
+  const int* rowseg;        // STATS: per frame utterance id, < 0 for halo rows
+  const float* bias;        // per column (STATS: per unit = per row)
   const float* scale;
   const float* offset;
+  const float* row_add;     // F32 mode: per-row addend or nullptr
   int relu;
   void* out;                // bf16 or fp32, row-major
   long long out_ld;
+  float* sums;              // STATS: (batch, 2, m_rows) raw sum / sum of squares of relu(acc + bias)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -97,7 +115,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// K-major, 128B-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
+// K-major, 128B-swizzled operand tile: rows of 64 16-bit elements (128 B), 8-row groups 1024 B apart.
 __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
   unsigned long long d = 0;
   d |= (unsigned long long)((smem_addr & 0x3FFFF) >> 4);
@@ -107,8 +125,8 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
   return d;
 }
 
-__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
-                                          unsigned idesc, unsigned accumulate) {
+__device__ __forceinline__ void umma_f16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                         unsigned idesc, unsigned accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -125,8 +143,10 @@ __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
-  unsigned r[32];
+// Asynchronous TMEM -> register load of 32 consecutive columns of this thread's lane.  The registers
+// may only be read after tmem_ld_wait(), which names them as in/out operands so that the compiler
+// cannot move their uses above the wait.
+__device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -136,9 +156,14 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait(unsigned (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
 }
 
 template <bool OUT_BF16>
@@ -179,7 +204,21 @@ __device__ __forceinline__ void store_row32(void* out, long long ld, long long r
   }
 }
 
-template <bool OUT_BF16>
+// Tile walk: row-storing modes go n-fastest (the n-tiles of one row block run on neighbouring CTAs and
+// share the activation rows through L2); STATS goes m-fastest (the unit tiles of one frame block).
+template <int MODE>
+__device__ __forceinline__ void tile_coords(long long tile, long long m_tiles, int n_tiles, long long& mt, int& nt) {
+  if (MODE == kModeStats) {
+    const long long q = tile / m_tiles;
+    mt = tile - q * m_tiles;
+    nt = (int)q;
+  } else {
+    mt = tile / n_tiles;
+    nt = (int)(tile - mt * n_tiles);
+  }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -194,10 +233,11 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   unsigned long long* tempty_bar = tfull_bar + kAccStages;   // [kAccStages]
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty_bar + kAccStages);
   float* s_vec = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [kAccStages][3][BN]
+  int* s_seg = reinterpret_cast<int*>(smem + kStages * kStageBytes + 256 + kVecBytes);  // [kAccStages][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m_tiles = (a.m_rows + BM - 1) / BM;
-  const int n_tiles = (a.n_cols + BN - 1) / BN;
+  const int n_tiles = (int)((a.n_rows + BN - 1) / BN);
   const long long total_tiles = m_tiles * n_tiles;
   const int num_kb = a.num_taps * a.kblocks_per_tap;
 
@@ -208,7 +248,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -230,16 +270,23 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       unsigned phase = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const long long mt = tile / n_tiles;
-        const int nt = (int)(tile - mt * n_tiles);
-        const int row0 = (int)(mt * BM), col0 = nt * BN;
+        long long mt;
+        int nt;
+        tile_coords<MODE>(tile, m_tiles, n_tiles, mt, nt);
+        const int m0 = (int)(mt * BM), n0 = nt * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / a.kblocks_per_tap;
           const int d0 = (kb - tap * a.kblocks_per_tap) * BK;
+          const int wcol = tap * a.tap_cols + d0;          // column in the weight matrix
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kStageBytes);
-          tma_load_2d(sA + stage * kABytes, &tmA, &full_bar[stage], d0, row0 + a.ctx[tap]);
-          tma_load_2d(sB + stage * kBBytes, &tmB, &full_bar[stage], tap * a.tap_cols + d0, col0);
+          if (a.shift_b) {
+            tma_load_2d(sA + stage * kABytes, &tmA, &full_bar[stage], wcol, m0);
+            tma_load_2d(sB + stage * kBBytes, &tmB, &full_bar[stage], d0, n0 + a.ctx[tap]);
+          } else {
+            tma_load_2d(sA + stage * kABytes, &tmA, &full_bar[stage], d0, m0 + a.ctx[tap]);
+            tma_load_2d(sB + stage * kBBytes, &tmB, &full_bar[stage], wcol, n0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -247,7 +294,9 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) |
+      // instruction descriptor: D fp32, A/B bf16 (format 1) or fp16 (format 0), both K-major, N, M
+      const unsigned fmt = a.fp16 ? 0u : 1u;
+      const unsigned idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(BN >> 3) << 17) |
                              ((unsigned)(BM >> 4) << 24);
       int stage = 0;
       unsigned phase = 0;
@@ -265,9 +314,9 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const unsigned long long bdesc = umma_desc(smem_u32(sB + stage * kBBytes));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the swizzled row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + (unsigned long long)(2 * k), bdesc + (unsigned long long)(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            // advance 16 elements = 32 bytes inside the swizzled row: +2 in the (addr >> 4) field
+            umma_f16(tmem_d, adesc + (unsigned long long)(2 * k), bdesc + (unsigned long long)(2 * k), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);     // frees the smem slot once these MMAs have read it
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -276,51 +325,135 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ================= epilogue warps (2..5) =================
+    // ================= epilogue warps (2..9) =================
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;          // 0..127
+    const int half = (warp - 2) >> 2;         // which 128 of the tile's 256 columns
+    const int et = threadIdx.x - 64;          // 0..255
     int it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const long long mt = tile / n_tiles;
-      const int nt = (int)(tile - mt * n_tiles);
+      long long mt;
+      int nt;
+      tile_coords<MODE>(tile, m_tiles, n_tiles, mt, nt);
       const int col_base = nt * BN;
       const int acc = it & 1;
       const unsigned acc_phase = (unsigned)(it >> 1) & 1u;
-      float* vb = s_vec + acc * 3 * BN;
-      // per-column epilogue vectors for this n-tile (double buffered with the accumulator stage)
-      for (int c = et; c < BN; c += 128) {
-        const int col = col_base + c;
-        const bool ok = col < a.n_cols;
-        vb[c] = (ok && a.bias) ? a.bias[col] : 0.0f;
-        vb[BN + c] = (ok && a.scale) ? a.scale[col] : 1.0f;
-        vb[2 * BN + c] = (ok && a.offset) ? a.offset[col] : 0.0f;
-      }
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-
       const long long row = mt * BM + quarter * 32 + lane;
-      int flags = 0;
-      if (row < a.m_rows) flags = a.rowmap ? a.rowmap[row] : kRowStore;
-      const unsigned taddr0 = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * BN);
-      for (int cc = 0; cc < BN; cc += 32) {
-        if (col_base + cc >= a.n_cols) break;           // warp-uniform
-        float v[32];
-        tmem_ld32(taddr0 + (unsigned)cc, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = v[i] + vb[cc + i];
-          if (a.relu) t = fmaxf(t, 0.0f);
-          v[i] = fmaf(t, vb[BN + cc + i], vb[2 * BN + cc + i]);
+      const unsigned taddr0 =
+          tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * BN) + (unsigned)(half * (BN / 2));
+
+      if (MODE == kModeStats) {
+        // ---- per-unit running sums over the frames of the tile (stats_pooling.py:228-240) ----
+        int* seg = s_seg + acc * BN;
+        {
+          const long long fr = (long long)col_base + et;
+          seg[et] = (fr < a.n_rows) ? a.rowseg[fr] : -1;
         }
-        if (flags & kRowStore) {
-          store_row32<OUT_BF16>(a.out, a.out_ld, row, col_base + cc, a.n_cols, v);
-          if (flags & kRowFirst)
-            for (int h = 1; h <= kHalo; ++h)
-              store_row32<OUT_BF16>(a.out, a.out_ld, row - h, col_base + cc, a.n_cols, v);
-          if (flags & kRowLast)
-            for (int h = 1; h <= kHalo; ++h)
-              store_row32<OUT_BF16>(a.out, a.out_ld, row + h, col_base + cc, a.n_cols, v);
+        const bool unit_ok = row < a.m_rows;
+        const float b = (unit_ok && a.bias) ? a.bias[row] : 0.0f;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+
+        const int* sg = seg + half * (BN / 2);
+        float s = 0.0f, s2 = 0.0f;
+        int cur = -1;
+        auto flush = [&]() {
+          if (cur >= 0 && unit_ok) {
+            atomicAdd(a.sums + ((long long)cur * 2 + 0) * a.m_rows + row, s);
+            atomicAdd(a.sums + ((long long)cur * 2 + 1) * a.m_rows + row, s2);
+          }
+        };
+        unsigned r[2][32];
+        tmem_ld32_issue(taddr0, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait(r[c & 1]);
+          if (c + 1 < 4) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) & 1]);
+          const int* sc = sg + c * 32;
+          const int first = sc[0], last = sc[31];
+          if (first == last && first >= 0) {   // warp-uniform: the whole chunk lies inside one utterance
+            if (first != cur) { flush(); cur = first; s = 0.0f; s2 = 0.0f; }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float t = __uint_as_float(r[c & 1][i]) + b;
+              if (a.relu) t = fmaxf(t, 0.0f);
+              s += t;
+              s2 = fmaf(t, t, s2);
+            }
+          } else {                             // utterance boundary / halo rows inside the chunk
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int u = sc[i];
+              if (u >= 0) {
+                if (u != cur) { flush(); cur = u; s = 0.0f; s2 = 0.0f; }
+                float t = __uint_as_float(r[c & 1][i]) + b;
+                if (a.relu) t = fmaxf(t, 0.0f);
+                s += t;
+                s2 = fmaf(t, t, s2);
+              }
+            }
+          }
+        }
+        flush();
+      } else {
+        // ---- bias / ReLU / BatchNorm per column, rows stored as bf16 or fp32 ----
+        float* vb = s_vec + acc * 3 * BN;
+        {
+          const int col = col_base + et;
+          const bool ok = col < a.n_rows;
+          vb[et] = (ok && a.bias) ? a.bias[col] : 0.0f;
+          vb[BN + et] = (ok && a.scale) ? a.scale[col] : 1.0f;
+          vb[2 * BN + et] = (ok && a.offset) ? a.offset[col] : 0.0f;
+        }
+        int flags = 0;
+        if (row < a.m_rows) flags = a.rowmap ? a.rowmap[row] : kRowStore;
+        float radd = 0.0f;
+        if (MODE == kModeF32 && a.row_add != nullptr && row < a.m_rows) radd = a.row_add[row];
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+
+        const int n_cols = (int)a.n_rows;
+        unsigned r[2][32];
+        tmem_ld32_issue(taddr0, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait(r[c & 1]);
+          if (c + 1 < 4) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) & 1]);
+          const int cc = half * (BN / 2) + c * 32;        // column offset inside the tile
+          if (col_base + cc < n_cols) {                   // warp-uniform
+            float v[32];
+            const float4* b4 = reinterpret_cast<const float4*>(vb + cc);
+            const float4* s4 = reinterpret_cast<const float4*>(vb + BN + cc);
+            const float4* o4 = reinterpret_cast<const float4*>(vb + 2 * BN + cc);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 bb = b4[q], ss = s4[q], oo = o4[q];
+              float t0 = __uint_as_float(r[c & 1][4 * q + 0]) + bb.x;
+              float t1 = __uint_as_float(r[c & 1][4 * q + 1]) + bb.y;
+              float t2 = __uint_as_float(r[c & 1][4 * q + 2]) + bb.z;
+              float t3 = __uint_as_float(r[c & 1][4 * q + 3]) + bb.w;
+              if (a.relu) {
+                t0 = fmaxf(t0, 0.0f);
+                t1 = fmaxf(t1, 0.0f);
+                t2 = fmaxf(t2, 0.0f);
+                t3 = fmaxf(t3, 0.0f);
+              }
+              v[4 * q + 0] = fmaf(t0, ss.x, oo.x) + radd;
+              v[4 * q + 1] = fmaf(t1, ss.y, oo.y) + radd;
+              v[4 * q + 2] = fmaf(t2, ss.z, oo.z) + radd;
+              v[4 * q + 3] = fmaf(t3, ss.w, oo.w) + radd;
+            }
+            if (flags & kRowStore) {
+              store_row32<MODE == kModeBf16>(a.out, a.out_ld, row, col_base + cc, n_cols, v);
+              if (flags & kRowFirst)
+                for (int h = 1; h <= kHalo; ++h)
+                  store_row32<MODE == kModeBf16>(a.out, a.out_ld, row - h, col_base + cc, n_cols, v);
+              if (flags & kRowLast)
+                for (int h = 1; h <= kHalo; ++h)
+                  store_row32<MODE == kModeBf16>(a.out, a.out_ld, row + h, col_base + cc, n_cols, v);
+            }
+          }
         }
       }
       tc_fence_before();
@@ -341,9 +474,11 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------
 
 // Padded-row bookkeeping of a ragged batch: utterance b owns padded rows
-// [poffs[b], poffs[b+1]) = kHalo + T_b + kHalo rows.  rowmap flags per padded row.
+// [poffs[b], poffs[b+1]) = kHalo + T_b + kHalo rows.  rowmap: flags per padded row; rowseg: utterance id of
+// real rows, -1 - id for halo rows.
 __global__ void build_padded_kernel(const long long* __restrict__ offs, long long batch,
-                                    long long* __restrict__ poffs, int* __restrict__ rowmap) {
+                                    long long* __restrict__ poffs, int* __restrict__ rowmap,
+                                    int* __restrict__ rowseg) {
   // one CTA per utterance
   const long long b = blockIdx.x;
   const long long r0 = offs[b], T = offs[b + 1] - r0;
@@ -355,91 +490,83 @@ __global__ void build_padded_kernel(const long long* __restrict__ offs, long lon
   for (long long i = threadIdx.x; i < T + 2 * kHalo; i += blockDim.x) {
     int f = 0;
     const long long t = i - kHalo;
-    if (t >= 0 && t < T) {
+    const bool real = t >= 0 && t < T;
+    if (real) {
       f = kRowStore;
       if (t == 0) f |= kRowFirst;
       if (t == T - 1) f |= kRowLast;
     }
     rowmap[p0 + i] = f;
+    rowseg[p0 + i] = real ? (int)b : -1 - (int)b;
   }
 }
 
 // Materialised splice ("im2col") for layers whose feature dimension is not a multiple of 64:
 // out[p, k*D + d] = x[clamp(t + ctx_k)] for every padded row p (halo rows clamp to the edge frames),
-// bf16, row stride ld (zero padded).  x is fp32 (rows, D) or bf16 padded-row (prow, D).
+// bf16, row stride ld (a multiple of 8, zero padded).  x is fp32 ragged (rows, D) or bf16 padded-row
+// (prow, x_ld).  One thread produces 8 consecutive outputs (one 16-byte store).
 template <typename TIn>
 __global__ void splice_kernel(const TIn* __restrict__ x, int D, long long x_ld, int x_is_padded,
                               const long long* __restrict__ offs, const long long* __restrict__ poffs,
-                              long long batch, int num_taps, const int* __restrict__ ctx_dev,
-                              __nv_bfloat16* __restrict__ out, long long ld) {
-  // grid: (padded rows), block: 128 threads over the K*D columns
+                              const int* __restrict__ rowseg, long long prow, int num_taps,
+                              const int* __restrict__ ctx_dev, __nv_bfloat16* __restrict__ out, long long ld) {
   __shared__ int s_ctx[KTF_MAX_CONTEXT];
-  if (threadIdx.x < num_taps) s_ctx[threadIdx.x] = ctx_dev[threadIdx.x];
+  if (threadIdx.x < KTF_MAX_CONTEXT) s_ctx[threadIdx.x] = threadIdx.x < num_taps ? ctx_dev[threadIdx.x] : 0;
   __syncthreads();
-  const long long p = blockIdx.x;
-  long long lo = 0, hi = batch;
-  while (hi - lo > 1) {
-    const long long mid = (lo + hi) >> 1;
-    if (poffs[mid] <= p) lo = mid; else hi = mid;
-  }
-  const long long T = offs[lo + 1] - offs[lo];
-  long long t = p - poffs[lo] - kHalo;
-  t = min(max(t, 0LL), T - 1);
-  const long long base = x_is_padded ? (poffs[lo] + kHalo) : offs[lo];
-  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
-    float v = 0.0f;
-    if (c < num_taps * D) {
-      const int k = c / D, d = c - k * D;
-      const long long tt = min(max(t + s_ctx[k], 0LL), T - 1);
-      v = (float)x[(base + tt) * x_ld + d];
+  const int chunks = (int)(ld >> 3);
+  const long long total = prow * chunks;
+  const int cols = num_taps * D;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long p = idx / chunks;
+    const int c0 = (int)(idx - p * chunks) << 3;
+    const int sgn = rowseg[p];
+    const int b = sgn >= 0 ? sgn : -1 - sgn;
+    const long long p0 = poffs[b];
+    const long long T = poffs[b + 1] - p0 - 2 * kHalo;
+    long long t = p - p0 - kHalo;
+    t = min(max(t, 0LL), T - 1);
+    const long long base = x_is_padded ? (p0 + kHalo) : offs[b];
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      float f = 0.0f;
+      if (c < cols) {
+        const int k = c / D, d = c - k * D;
+        const long long tt = min(max(t + s_ctx[k], 0LL), T - 1);
+        f = (float)x[(base + tt) * x_ld + d];
+      }
+      v[i] = __float2bfloat16_rn(f);
     }
-    out[p * ld + c] = __float2bfloat16_rn(v);
+    *reinterpret_cast<uint4*>(out + p * ld + c0) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
-// Per-utterance sum / sum of squares over the real (non-halo) rows of a padded bf16 activation matrix,
-// then mean || std (stats_pooling.py:228-240) written as bf16 (next GEMM operand) and/or fp32.
-__global__ void stats_padded_kernel(const __nv_bfloat16* __restrict__ y, long long ld, int dim,
-                                    const long long* __restrict__ poffs, int include_std, float eps,
-                                    __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
-                                    long long out_ld) {
-  const int d = blockIdx.y * blockDim.x + threadIdx.x;
-  if (d >= dim) return;
+// (batch, 2, U) raw sums of r = relu(acc + bias) over the frames of each utterance -> mean || std of
+// y = scale * r + offset (batchnorm.py:81-88 folded in algebraically; stats_pooling.py:228-240):
+//   mean_y = scale * mean_r + offset,  var_y = scale^2 * (E[r^2] - mean_r^2),  std = sqrt(relu(var_y) + eps)
+__global__ void stats_finalize_tc_kernel(const float* __restrict__ sums, const long long* __restrict__ offs, int U,
+                                         const float* __restrict__ scale, const float* __restrict__ offset,
+                                         int include_std, float eps, __nv_bfloat16* __restrict__ out_bf16,
+                                         float* __restrict__ out_f32, long long out_ld) {
+  const int u = blockIdx.y * blockDim.x + threadIdx.x;
+  if (u >= U) return;
   const long long b = blockIdx.x;
-  const long long r0 = poffs[b] + kHalo, r1 = poffs[b + 1] - kHalo;
-  float s = 0.0f, s2 = 0.0f, cs = 0.0f, cs2 = 0.0f;          // Kahan-compensated fp32 sums
-  for (long long r = r0; r < r1; ++r) {
-    const float v = __bfloat162float(y[r * ld + d]);
-    float yk = v - cs, tk = s + yk;
-    cs = (tk - s) - yk;
-    s = tk;
-    yk = v * v - cs2;
-    tk = s2 + yk;
-    cs2 = (tk - s2) - yk;
-    s2 = tk;
-  }
-  const float n = (float)(r1 - r0);
-  const float mean = s / n;
-  const float var = s2 / n - __fmul_rn(mean, mean);
-  const float sd = sqrtf(fmaxf(var, 0.0f) + eps);
+  const float n = (float)(offs[b + 1] - offs[b]);
+  const float mr = sums[(b * 2 + 0) * U + u] / n;
+  const float vr = sums[(b * 2 + 1) * U + u] / n - __fmul_rn(mr, mr);
+  const float sc = scale ? scale[u] : 1.0f;
+  const float of = offset ? offset[u] : 0.0f;
+  const float mean = fmaf(sc, mr, of);
+  const float sd = sqrtf(fmaxf(sc * sc * vr, 0.0f) + eps);
   if (out_bf16) {
-    out_bf16[b * out_ld + d] = __float2bfloat16_rn(mean);
-    if (include_std) out_bf16[b * out_ld + dim + d] = __float2bfloat16_rn(sd);
+    out_bf16[b * out_ld + u] = __float2bfloat16_rn(mean);
+    if (include_std) out_bf16[b * out_ld + U + u] = __float2bfloat16_rn(sd);
   }
   if (out_f32) {
-    out_f32[b * out_ld + d] = mean;
-    if (include_std) out_f32[b * out_ld + dim + d] = sd;
-  }
-}
-
-__global__ void f32_to_bf16_rows_kernel(const float* __restrict__ x, long long rows, int dim, long long ld,
-                                        __nv_bfloat16* __restrict__ out) {
-  const long long total = rows * ld;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / ld;
-    const int c = (int)(i - r * ld);
-    out[i] = __float2bfloat16_rn(c < dim ? x[r * dim + c] : 0.0f);
+    out_f32[b * out_ld + u] = mean;
+    if (include_std) out_f32[b * out_ld + U + u] = sd;
   }
 }
 
@@ -467,7 +594,9 @@ struct TcLayer {
   long long w_ld = 0;               // bf16 weight row stride (elements)
   __nv_bfloat16* d_w = nullptr;     // (U, w_ld)
   int* d_ctx = nullptr;
-  CUtensorMap tmB;
+  CUtensorMap tmW_n;                // weights as the B operand (box BK x BN)
+  CUtensorMap tmW_m;                // weights as the A operand (box BK x BM), STATS mode
+  ktf::Workspace ws;                // scratch of the stand-alone layer call
 };
 
 // cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so that the
@@ -488,6 +617,8 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// 2-D map over a row-major 16-bit matrix (inner = columns); OOB boxes (negative or past-the-end rows /
+// columns) are zero filled.  bf16 and fp16 share the map type: TMA only moves the bytes.
 int encode_map(CUtensorMap* map, const void* base, unsigned long long inner, unsigned long long rows,
                unsigned long long ld_elems, unsigned box_inner, unsigned box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
@@ -516,7 +647,7 @@ int check_arch() {
   static int arch = 0;
   if (arch == 0) arch = ktf_device_arch();
   if (arch < 100) {
-    ktf::set_error("the tcgen05 TDNN engine needs an sm_100 device (found sm_%d)", arch);
+    ktf::set_error("the tcgen05 engine needs an sm_100 device (found sm_%d)", arch);
     return KTF_EINVAL;
   }
   return KTF_OK;
@@ -538,40 +669,36 @@ int prepare_layer(TcLayer* L, const ktf_affine_cfg& c, const float* w_host) {
   int rc;
   if ((rc = ktf::upload(&L->d_w, wb.data(), wb.size())) != KTF_OK) return rc;
   if ((rc = ktf::upload(&L->d_ctx, L->ctx, (size_t)KTF_MAX_CONTEXT)) != KTF_OK) return rc;
-  return encode_map(&L->tmB, L->d_w, (unsigned long long)cols, (unsigned long long)c.out_dim,
-                    (unsigned long long)L->w_ld, BK, BN);
+  if ((rc = encode_map(&L->tmW_n, L->d_w, (unsigned long long)cols, (unsigned long long)c.out_dim,
+                       (unsigned long long)L->w_ld, BK, BN)) != KTF_OK)
+    return rc;
+  return encode_map(&L->tmW_m, L->d_w, (unsigned long long)cols, (unsigned long long)c.out_dim,
+                    (unsigned long long)L->w_ld, BK, BM);
 }
 
 void release_layer(TcLayer* L) {
   if (!L) return;
   cudaFree(L->d_w);
   cudaFree(L->d_ctx);
+  L->ws.release();
 }
 
-template <bool OUT_BF16>
+template <int MODE>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    KTF_CUDA(cudaFuncSetAttribute(tdnn_tc_kernel<OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc));
+    KTF_CUDA(cudaFuncSetAttribute(tdnn_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc));
     attr_done = true;
   }
-  const long long tiles = ((args.m_rows + BM - 1) / BM) * ((args.n_cols + BN - 1) / BN);
+  const long long tiles = ((args.m_rows + BM - 1) / BM) * ((args.n_rows + BN - 1) / BN);
   if (tiles <= 0) return KTF_OK;
   const unsigned grid = (unsigned)std::min<long long>(tiles, ktf::num_sms());
-  tdnn_tc_kernel<OUT_BF16><<<grid, kThreadsTc, kSmemTc, st>>>(tmA, tmB, args);
+  tdnn_tc_kernel<MODE><<<grid, kThreadsTc, kSmemTc, st>>>(tmA, tmB, args);
   KTF_LAUNCH_OK();
   return KTF_OK;
 }
 
-// One affine layer on padded rows.  in: bf16 (prow, in_ld) padded-row activations, or (for !implicit)
-// any source handled by the caller through `spliced`.
-int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, long long a_ld, long long a_cols,
-              long long m_rows, const int* rowmap, void* out, long long out_ld, bool out_bf16, bool a_is_spliced,
-              cudaStream_t st) {
-  CUtensorMap tmA;
-  int rc = encode_map(&tmA, A, (unsigned long long)a_cols, (unsigned long long)m_rows, (unsigned long long)a_ld, BK, BM);
-  if (rc != KTF_OK) return rc;
-  TcArgs args{};
+void fill_taps(TcArgs& args, const TcLayer& L, bool a_is_spliced, long long a_cols) {
   if (a_is_spliced) {
     args.num_taps = 1;
     args.ctx[0] = 0;
@@ -583,8 +710,20 @@ int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, lon
     args.kblocks_per_tap = L.D / BK;
     args.tap_cols = L.D;
   }
+}
+
+// One affine layer on padded rows, output stored row-major.  A: bf16 (m_rows, a_ld) padded-row activations
+// (implicit taps) or an already spliced matrix.
+int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, long long a_ld, long long a_cols,
+              long long m_rows, const int* rowmap, void* out, long long out_ld, bool out_bf16, bool a_is_spliced,
+              cudaStream_t st) {
+  CUtensorMap tmA;
+  int rc = encode_map(&tmA, A, (unsigned long long)a_cols, (unsigned long long)m_rows, (unsigned long long)a_ld, BK, BM);
+  if (rc != KTF_OK) return rc;
+  TcArgs args{};
+  fill_taps(args, L, a_is_spliced, a_cols);
   args.m_rows = m_rows;
-  args.n_cols = L.U;
+  args.n_rows = L.U;
   args.rowmap = rowmap;
   args.bias = a->d_bias;
   args.scale = a->d_scale;
@@ -592,7 +731,30 @@ int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, lon
   args.relu = a->cfg.activation == KTF_ACT_RELU;
   args.out = out;
   args.out_ld = out_ld;
-  return out_bf16 ? launch_gemm<true>(tmA, L.tmB, args, st) : launch_gemm<false>(tmA, L.tmB, args, st);
+  return out_bf16 ? launch_gemm<kModeBf16>(tmA, L.tmW_n, args, st) : launch_gemm<kModeF32>(tmA, L.tmW_n, args, st);
+}
+
+// The layer that feeds StatsPooling: operands swapped (M = units, N = frames), epilogue accumulates
+// per-utterance sum / sum of squares of relu(acc + bias) into sums (batch, 2, U) (pre-zeroed).
+int run_layer_stats(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* X, long long x_ld, long long x_cols,
+                    long long frames, const int* rowseg, float* sums, bool x_is_spliced, cudaStream_t st) {
+  CUtensorMap tmX;
+  int rc = encode_map(&tmX, X, (unsigned long long)x_cols, (unsigned long long)frames, (unsigned long long)x_ld, BK, BN);
+  if (rc != KTF_OK) return rc;
+  TcArgs args{};
+  fill_taps(args, L, x_is_spliced, x_cols);
+  args.shift_b = 1;
+  args.m_rows = L.U;
+  args.n_rows = frames;
+  args.rowseg = rowseg;
+  args.bias = a->d_bias;
+  args.relu = a->cfg.activation == KTF_ACT_RELU;
+  args.sums = sums;
+  return launch_gemm<kModeStats>(L.tmW_m, tmX, args, st);
+}
+
+unsigned blocks_for(long long items, int threads) {
+  return (unsigned)std::min<long long>((items + threads - 1) / threads, (long long)ktf::num_sms() * 16);
 }
 
 }  // namespace
@@ -626,42 +788,68 @@ void affine_tc_release(ktf_affine* a) {
 int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in_offsets_dev,
                       const int64_t* out_offsets_dev, int64_t batch, int64_t total_in_rows,
                       int64_t total_out_rows, float* y_dev, float* stats_dev, cudaStream_t st) {
-  const TcLayer& L = *static_cast<const TcLayer*>(a->tc);
+  TcLayer& L = *static_cast<TcLayer*>(a->tc);
   KTF_CHECK_ARG(!a->cfg.padding_valid && a->cfg.subsampling_factor == 1,
                 "KTF_PREC_BF16 supports padding=SAME, subsampling_factor=1 (use KTF_PREC_F32 otherwise)");
   KTF_CHECK_ARG(total_in_rows == total_out_rows, "row count mismatch");
   (void)out_offsets_dev;
   const long long prow = total_in_rows + 2LL * kHalo * batch;
   const long long cols = (long long)L.K * L.D, ld = round_up(cols, 8);
-  long long* poffs = nullptr;
-  int* rowmap = nullptr;
-  __nv_bfloat16* spliced = nullptr;
-  float* yp = nullptr;
-  KTF_CUDA(cudaMallocAsync((void**)&poffs, (batch + 1) * sizeof(long long), st));
-  KTF_CUDA(cudaMallocAsync((void**)&rowmap, prow * sizeof(int), st));
-  KTF_CUDA(cudaMallocAsync((void**)&spliced, (size_t)prow * ld * sizeof(__nv_bfloat16), st));
-  KTF_CUDA(cudaMallocAsync((void**)&yp, (size_t)prow * L.U * sizeof(float), st));
-  build_padded_kernel<<<(unsigned)batch, 128, 0, st>>>((const long long*)in_offsets_dev, batch, poffs, rowmap);
-  KTF_LAUNCH_OK();
-  splice_kernel<float><<<(unsigned)prow, 128, 0, st>>>(x_dev, L.D, L.D, 0, (const long long*)in_offsets_dev, poffs,
-                                                       batch, L.K, L.d_ctx, spliced, ld);
-  KTF_LAUNCH_OK();
-  int rc = run_layer(L, a, spliced, ld, cols, prow, rowmap, yp, L.U, /*out_bf16=*/false, /*spliced=*/true, st);
+  ktf::Carver cv;
+  const size_t o_poffs = cv.take((batch + 1) * sizeof(long long));
+  const size_t o_rowmap = cv.take(prow * sizeof(int));
+  const size_t o_rowseg = cv.take(prow * sizeof(int));
+  const size_t o_spliced = cv.take((size_t)prow * ld * sizeof(__nv_bfloat16));
+  const size_t o_yp = cv.take((size_t)prow * L.U * sizeof(float));
+  const size_t o_y = cv.take(y_dev ? 0 : (size_t)total_out_rows * L.U * sizeof(float));
+  int rc = L.ws.ensure(cv.off);
   if (rc != KTF_OK) return rc;
-  float* y = y_dev;
-  if (y == nullptr) KTF_CUDA(cudaMallocAsync((void**)&y, (size_t)total_out_rows * L.U * sizeof(float), st));
+  char* base = static_cast<char*>(L.ws.ptr);
+  long long* poffs = reinterpret_cast<long long*>(base + o_poffs);
+  int* rowmap = reinterpret_cast<int*>(base + o_rowmap);
+  int* rowseg = reinterpret_cast<int*>(base + o_rowseg);
+  __nv_bfloat16* spliced = reinterpret_cast<__nv_bfloat16*>(base + o_spliced);
+  float* yp = reinterpret_cast<float*>(base + o_yp);
+  float* y = y_dev ? y_dev : reinterpret_cast<float*>(base + o_y);
+
+  build_padded_kernel<<<(unsigned)batch, 128, 0, st>>>((const long long*)in_offsets_dev, batch, poffs, rowmap, rowseg);
+  KTF_LAUNCH_OK();
+  splice_kernel<float><<<blocks_for(prow * (ld >> 3), 256), 256, 0, st>>>(
+      x_dev, L.D, L.D, 0, (const long long*)in_offsets_dev, poffs, rowseg, prow, L.K, L.d_ctx, spliced, ld);
+  KTF_LAUNCH_OK();
+  rc = run_layer(L, a, spliced, ld, cols, prow, rowmap, yp, L.U, /*out_bf16=*/false, /*spliced=*/true, st);
+  if (rc != KTF_OK) return rc;
   unpad_rows_kernel<<<(unsigned)batch, 256, 0, st>>>(yp, L.U, L.U, (const long long*)in_offsets_dev, poffs, batch, y);
   KTF_LAUNCH_OK();
   if (stats_dev) {
     rc = ktf::stats_sums_f32(y, in_offsets_dev, batch, L.U, stats_dev, st);
     if (rc != KTF_OK) return rc;
   }
-  if (y_dev == nullptr) KTF_CUDA(cudaFreeAsync(y, st));
-  KTF_CUDA(cudaFreeAsync(yp, st));
-  KTF_CUDA(cudaFreeAsync(spliced, st));
-  KTF_CUDA(cudaFreeAsync(rowmap, st));
-  KTF_CUDA(cudaFreeAsync(poffs, st));
   return KTF_OK;
+}
+
+// C[i, j] = sum_k A[i, k] * B[j, k] + row_add[i] + col_add[j], A (m, K) and B (n, K) row-major 16-bit
+// (bf16 or fp16), C fp32 with row stride ldc.  K and both leading dimensions must be multiples of 8.
+int tc_gemm_nt(const void* A, long long m, long long lda, const void* B, long long n, long long ldb, long long K,
+               int fp16, const float* row_add, const float* col_add, float* C, long long ldc, cudaStream_t st) {
+  int rc = check_arch();
+  if (rc != KTF_OK) return rc;
+  CUtensorMap tmA, tmB;
+  if ((rc = encode_map(&tmA, A, (unsigned long long)K, (unsigned long long)m, (unsigned long long)lda, BK, BM)) != KTF_OK)
+    return rc;
+  if ((rc = encode_map(&tmB, B, (unsigned long long)K, (unsigned long long)n, (unsigned long long)ldb, BK, BN)) != KTF_OK)
+    return rc;
+  TcArgs args{};
+  args.num_taps = 1;
+  args.kblocks_per_tap = (int)((K + BK - 1) / BK);
+  args.fp16 = fp16;
+  args.m_rows = m;
+  args.n_rows = n;
+  args.bias = col_add;
+  args.row_add = row_add;
+  args.out = C;
+  args.out_ld = ldc;
+  return launch_gemm<kModeF32>(tmA, tmB, args, st);
 }
 
 }  // namespace ktf
@@ -676,6 +864,7 @@ struct ktf_tdnn_stack {
   int stats_after = -1;                  // index of the layer followed by stats pooling (-1 = none)
   int include_std = 1;
   float stats_eps = 1e-10f;
+  ktf::Workspace ws;                     // activations, padded-row maps, statistics (grow-only)
 };
 
 extern "C" {
@@ -708,7 +897,11 @@ int ktf_tdnn_stack_create(ktf_affine* const* layers, int32_t num_layers, int32_t
   return KTF_OK;
 }
 
-void ktf_tdnn_stack_destroy(ktf_tdnn_stack* s) { delete s; }
+void ktf_tdnn_stack_destroy(ktf_tdnn_stack* s) {
+  if (!s) return;
+  s->ws.release();
+  delete s;
+}
 
 int32_t ktf_tdnn_stack_out_dim(const ktf_tdnn_stack* s) {
   if (!s) return 0;
@@ -717,122 +910,136 @@ int32_t ktf_tdnn_stack_out_dim(const ktf_tdnn_stack* s) {
   return dim;
 }
 
-int ktf_tdnn_stack_forward(const ktf_tdnn_stack* s, const float* feats_dev, const int64_t* offsets_dev,
+int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int64_t* offsets_dev,
                            int64_t batch, int64_t total_rows, float* out_dev, void* stream) {
   KTF_CHECK_ARG(s && feats_dev && offsets_dev && out_dev, "ktf_tdnn_stack_forward: null argument");
   if (batch <= 0 || total_rows <= 0) return KTF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const long long prow = total_rows + 2LL * kHalo * batch;
   const int nl = (int)s->layers.size();
+  const long long* offs = (const long long*)offsets_dev;
 
-  long long* poffs = nullptr;
-  int* rowmap = nullptr;
-  KTF_CUDA(cudaMallocAsync((void**)&poffs, (batch + 1) * sizeof(long long), st));
-  KTF_CUDA(cudaMallocAsync((void**)&rowmap, prow * sizeof(int), st));
-  build_padded_kernel<<<(unsigned)batch, 128, 0, st>>>((const long long*)offsets_dev, batch, poffs, rowmap);
-  KTF_LAUNCH_OK();
-
-  // activation ping-pong buffers sized for the widest layer
-  long long max_ld = 8;
+  // ---- workspace plan: per-frame activation ping-pong sized for the widest STORED matrix -------------
+  long long max_ld = 8, final_frame_dim = 0;
+  int stats_U = 0;
   for (int i = 0; i < nl; ++i) {
     const ktf_affine_cfg& c = s->layers[i]->cfg;
-    max_ld = std::max(max_ld, round_up((long long)c.num_context * c.in_dim, 8));
-    max_ld = std::max(max_ld, round_up(c.out_dim, 8));
+    const TcLayer& L = *static_cast<const TcLayer*>(s->layers[i]->tc);
+    const bool per_frame_in = (s->stats_after < 0) || (i <= s->stats_after);
+    if (per_frame_in && (i == 0 || !L.implicit)) max_ld = std::max(max_ld, round_up((long long)c.num_context * c.in_dim, 8));
+    const bool stored_bf16 = per_frame_in && i != s->stats_after && i != nl - 1;
+    if (stored_bf16) max_ld = std::max(max_ld, round_up(c.out_dim, 8));
+    if (i == s->stats_after) stats_U = c.out_dim;
+    if (i == nl - 1 && per_frame_in && i != s->stats_after) final_frame_dim = c.out_dim;
   }
-  __nv_bfloat16* buf[2] = {nullptr, nullptr};
-  KTF_CUDA(cudaMallocAsync((void**)&buf[0], (size_t)prow * max_ld * sizeof(__nv_bfloat16), st));
-  KTF_CUDA(cudaMallocAsync((void**)&buf[1], (size_t)prow * max_ld * sizeof(__nv_bfloat16), st));
-  __nv_bfloat16* pooled = nullptr;
+  const int pooled_dim = s->include_std ? 2 * stats_U : stats_U;
+  const long long p_ld = round_up(std::max(pooled_dim, 8), 8);
+  long long post_ld = 8;                                    // widest bf16 activation after pooling
+  for (int i = s->stats_after + 1; i < nl - 1 && s->stats_after >= 0; ++i)
+    post_ld = std::max(post_ld, round_up(s->layers[i]->cfg.out_dim, 8));
+
+  ktf::Carver cv;
+  const size_t o_poffs = cv.take((batch + 1) * sizeof(long long));
+  const size_t o_rowmap = cv.take(prow * sizeof(int));
+  const size_t o_rowseg = cv.take(prow * sizeof(int));
+  const size_t o_buf0 = cv.take((size_t)prow * max_ld * sizeof(__nv_bfloat16));
+  const size_t o_buf1 = cv.take((size_t)prow * max_ld * sizeof(__nv_bfloat16));
+  const size_t o_sums = cv.take((size_t)batch * 2 * std::max(stats_U, 1) * sizeof(float));
+  const size_t o_pooled = cv.take((size_t)batch * p_ld * sizeof(__nv_bfloat16));
+  const size_t o_post0 = cv.take((size_t)batch * post_ld * sizeof(__nv_bfloat16));
+  const size_t o_post1 = cv.take((size_t)batch * post_ld * sizeof(__nv_bfloat16));
+  const size_t o_yp = cv.take((size_t)prow * final_frame_dim * sizeof(float));
+  int rc = s->ws.ensure(cv.off);
+  if (rc != KTF_OK) return rc;
+  char* base = static_cast<char*>(s->ws.ptr);
+  long long* poffs = reinterpret_cast<long long*>(base + o_poffs);
+  int* rowmap = reinterpret_cast<int*>(base + o_rowmap);
+  int* rowseg = reinterpret_cast<int*>(base + o_rowseg);
+  __nv_bfloat16* buf[2] = {reinterpret_cast<__nv_bfloat16*>(base + o_buf0),
+                           reinterpret_cast<__nv_bfloat16*>(base + o_buf1)};
+  float* sums = reinterpret_cast<float*>(base + o_sums);
+  __nv_bfloat16* pooled = reinterpret_cast<__nv_bfloat16*>(base + o_pooled);
+  __nv_bfloat16* post[2] = {reinterpret_cast<__nv_bfloat16*>(base + o_post0),
+                            reinterpret_cast<__nv_bfloat16*>(base + o_post1)};
+  float* yp = reinterpret_cast<float*>(base + o_yp);
+
+  build_padded_kernel<<<(unsigned)batch, 128, 0, st>>>(offs, batch, poffs, rowmap, rowseg);
+  KTF_LAUNCH_OK();
 
   const __nv_bfloat16* cur = nullptr;   // current activations (bf16) and their geometry
-  long long cur_ld = 0, cur_rows = prow;
-  const int* cur_rowmap = rowmap;
+  long long cur_ld = 0;
   bool per_frame = true;                // false once stats pooling collapsed the time axis
-  int which = 0;
-  int rc = KTF_OK;
+  int which = 0, pwhich = 0;
 
-  for (int i = 0; i < nl && rc == KTF_OK; ++i) {
+  for (int i = 0; i < nl; ++i) {
     const ktf_affine* a = s->layers[i];
     const TcLayer& L = *static_cast<const TcLayer*>(a->tc);
     const long long cols = (long long)L.K * L.D;
-    const bool last = (i == nl - 1) && (s->stats_after != i);
+    const bool last = (i == nl - 1);
+
+    if (!per_frame) {
+      // pooled rows: a plain (batch x K) GEMM, context [0]
+      if (last) return run_layer(L, a, cur, cur_ld, L.D, batch, nullptr, out_dev, L.U, false, true, st);
+      __nv_bfloat16* y = post[pwhich];
+      const long long y_ld = round_up(L.U, 8);
+      if ((rc = run_layer(L, a, cur, cur_ld, L.D, batch, nullptr, y, y_ld, true, true, st)) != KTF_OK) return rc;
+      cur = y;
+      cur_ld = y_ld;
+      pwhich ^= 1;
+      continue;
+    }
+
+    // ---- operand of a per-frame layer: implicit taps on the padded activations, or a materialised splice
     const __nv_bfloat16* A = cur;
     long long a_ld = cur_ld, a_cols = L.D;
     bool spliced = false;
-    if (i == 0) {
-      // first layer: fp32 ragged features -> bf16 spliced padded rows (also covers D % 64 != 0)
+    if (i == 0 || !L.implicit) {
       __nv_bfloat16* sp = buf[which];
       const long long ld = round_up(cols, 8);
-      splice_kernel<float><<<(unsigned)prow, 128, 0, st>>>(feats_dev, L.D, L.D, 0, (const long long*)offsets_dev,
-                                                           poffs, batch, L.K, L.d_ctx, sp, ld);
+      const unsigned grid = blocks_for(prow * (ld >> 3), 256);
+      if (i == 0)
+        splice_kernel<float><<<grid, 256, 0, st>>>(feats_dev, L.D, L.D, 0, offs, poffs, rowseg, prow, L.K, L.d_ctx,
+                                                   sp, ld);
+      else
+        splice_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(cur, L.D, cur_ld, 1, offs, poffs, rowseg, prow, L.K,
+                                                           L.d_ctx, sp, ld);
       KTF_LAUNCH_OK();
       A = sp;
       a_ld = ld;
       a_cols = cols;
       spliced = true;
       which ^= 1;
-    } else if (per_frame && !L.implicit) {
-      __nv_bfloat16* sp = buf[which];
-      const long long ld = round_up(cols, 8);
-      splice_kernel<__nv_bfloat16><<<(unsigned)prow, 128, 0, st>>>(cur, L.D, cur_ld, 1, (const long long*)offsets_dev,
-                                                                   poffs, batch, L.K, L.d_ctx, sp, ld);
-      KTF_LAUNCH_OK();
-      A = sp;
-      a_ld = ld;
-      a_cols = cols;
-      spliced = true;
-      which ^= 1;
-    } else if (!per_frame) {
-      a_cols = L.D;          // context [0] on pooled rows
-      spliced = true;
     }
-    if (last) {
-      // final layer writes fp32; per-frame outputs are un-padded into the caller's layout
-      if (per_frame) {
-        float* yp = nullptr;
-        KTF_CUDA(cudaMallocAsync((void**)&yp, (size_t)prow * L.U * sizeof(float), st));
-        rc = run_layer(L, a, A, a_ld, a_cols, cur_rows, cur_rowmap, yp, L.U, false, spliced, st);
-        if (rc == KTF_OK) {
-          unpad_rows_kernel<<<(unsigned)batch, 256, 0, st>>>(yp, L.U, L.U, (const long long*)offsets_dev, poffs,
-                                                            batch, out_dev);
-          KTF_LAUNCH_OK();
-        }
-        KTF_CUDA(cudaFreeAsync(yp, st));
-      } else {
-        rc = run_layer(L, a, A, a_ld, a_cols, cur_rows, nullptr, out_dev, L.U, false, spliced, st);
-      }
-      break;
-    }
-    __nv_bfloat16* y = buf[which];
-    const long long y_ld = round_up(L.U, 8);
-    rc = run_layer(L, a, A, a_ld, a_cols, cur_rows, per_frame ? cur_rowmap : nullptr, y, y_ld, true, spliced, st);
-    if (rc != KTF_OK) break;
-    cur = y;
-    cur_ld = y_ld;
-    which ^= 1;
+
     if (i == s->stats_after) {
-      const int od = s->include_std ? 2 * L.U : L.U;
-      const long long p_ld = round_up(od, 8);
-      const bool final_stats = (i == nl - 1);
-      if (!final_stats) KTF_CUDA(cudaMallocAsync((void**)&pooled, (size_t)batch * p_ld * sizeof(__nv_bfloat16), st));
+      // fused StatsPooling: the activation of this layer is never stored
+      KTF_CUDA(cudaMemsetAsync(sums, 0, (size_t)batch * 2 * L.U * sizeof(float), st));
+      if ((rc = run_layer_stats(L, a, A, a_ld, a_cols, prow, rowseg, sums, spliced, st)) != KTF_OK) return rc;
       dim3 grid((unsigned)batch, (unsigned)((L.U + 127) / 128));
-      stats_padded_kernel<<<grid, 128, 0, st>>>(cur, cur_ld, L.U, poffs, s->include_std, s->stats_eps,
-                                                final_stats ? nullptr : pooled, final_stats ? out_dev : nullptr,
-                                                final_stats ? od : p_ld);
+      stats_finalize_tc_kernel<<<grid, 128, 0, st>>>(sums, offs, L.U, a->d_scale, a->d_offset, s->include_std,
+                                                     s->stats_eps, last ? nullptr : pooled, last ? out_dev : nullptr,
+                                                     last ? (long long)pooled_dim : p_ld);
       KTF_LAUNCH_OK();
       cur = pooled;
       cur_ld = p_ld;
-      cur_rows = batch;
       per_frame = false;
+      continue;
     }
+    if (last) {
+      // per-frame fp32 output, un-padded into the caller's ragged layout
+      if ((rc = run_layer(L, a, A, a_ld, a_cols, prow, rowmap, yp, L.U, false, spliced, st)) != KTF_OK) return rc;
+      unpad_rows_kernel<<<(unsigned)batch, 256, 0, st>>>(yp, L.U, L.U, offs, poffs, batch, out_dev);
+      KTF_LAUNCH_OK();
+      return KTF_OK;
+    }
+    __nv_bfloat16* y = buf[which];
+    const long long y_ld = round_up(L.U, 8);
+    if ((rc = run_layer(L, a, A, a_ld, a_cols, prow, rowmap, y, y_ld, true, spliced, st)) != KTF_OK) return rc;
+    cur = y;
+    cur_ld = y_ld;
+    which ^= 1;
   }
-
-  if (pooled) cudaFreeAsync(pooled, st);
-  cudaFreeAsync(buf[1], st);
-  cudaFreeAsync(buf[0], st);
-  cudaFreeAsync(rowmap, st);
-  cudaFreeAsync(poffs, st);
-  return rc;
+  return KTF_OK;
 }
 
 }  // extern "C"
