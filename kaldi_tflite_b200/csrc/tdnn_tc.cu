@@ -48,7 +48,9 @@ constexpr int kBBytes = BN * BK * 2;                 // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kVecBytes = kAccStages * 3 * BN * 4;   // epilogue vectors (bias / scale / offset)
 constexpr int kSegBytes = kAccStages * BN * 4;       // STATS: utterance id of every frame of the tile
-constexpr int kSmemTc = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kVecBytes + kSegBytes;
+constexpr int kStgPitch = 80;                        // bytes per staged row: 64 B payload + 16 B (bank spread)
+constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch;  // per-warp 32 x 64 B transpose buffers for coalesced stores
+constexpr int kSmemTc = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kVecBytes + kSegBytes + kStgBytes;
 
 enum { kModeBf16 = 0, kModeF32 = 1, kModeStats = 2 };
 
@@ -166,41 +168,69 @@ __device__ __forceinline__ void tmem_ld_wait(unsigned (&r)[32]) {
                  "+r"(r[29]), "+r"(r[30]), "+r"(r[31])::"memory");
 }
 
+__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<unsigned*>(&h);
+}
+
+// One 32-column chunk of a warp's 32 accumulator rows: y = scale * max(acc + bias, relu_lo) + offset (+ radd).
+// A thread owns one ROW of the accumulator (TMEM lane), so storing straight from registers would make every
+// warp-wide store touch 32 different rows with 16 bytes each (32 partial sectors per instruction -- measured
+// as the bottleneck of the K <= 512 layers).  The chunk is therefore transposed through a per-warp staging
+// buffer in 64-byte row segments (32 bf16 / 16 fp32 columns): lanes write their own row, then 4 consecutive
+// lanes read back one row segment, so a warp store covers 8 rows x 64 contiguous bytes (16 full sectors).
+// Rows flagged first / last also write their kHalo replicas; rows without kRowStore are skipped.
 template <bool OUT_BF16>
-__device__ __forceinline__ void store_row32(void* out, long long ld, long long row, int col0, int n_cols,
-                                            const float (&v)[32]) {
-  if (OUT_BF16) {
-    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(out) + row * ld + col0;
-    if (col0 + 32 <= n_cols && ((reinterpret_cast<unsigned long long>(p) & 15ull) == 0)) {
+__device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float* vb, float relu_lo, float radd,
+                                            unsigned char* stg, int lane, int flags, unsigned char* out0,
+                                            long long ld_bytes) {
+  const float4* b4 = reinterpret_cast<const float4*>(vb);
+  const float4* s4 = reinterpret_cast<const float4*>(vb + BN);
+  const float4* o4 = reinterpret_cast<const float4*>(vb + 2 * BN);
+  constexpr int kPasses = OUT_BF16 ? 1 : 2;     // 64-byte segments per 32-column chunk
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 pk;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-        pk.x = *reinterpret_cast<unsigned*>(&h0);
-        pk.y = *reinterpret_cast<unsigned*>(&h1);
-        pk.z = *reinterpret_cast<unsigned*>(&h2);
-        pk.w = *reinterpret_cast<unsigned*>(&h3);
-        reinterpret_cast<uint4*>(p)[q] = pk;
+  for (int pass = 0; pass < kPasses; ++pass) {
+    uint4* mine = reinterpret_cast<uint4*>(stg + lane * kStgPitch);
+#pragma unroll
+    for (int g = 0; g < (OUT_BF16 ? 4 : 2); ++g) {      // 8 columns per group
+      const int c8 = OUT_BF16 ? g : 2 * pass + g;       // which group of 8 columns of the chunk
+      float x[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 bb = b4[2 * c8 + h], ss = s4[2 * c8 + h], oo = o4[2 * c8 + h];
+        x[4 * h + 0] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 0]) + bb.x, relu_lo), ss.x, oo.x);
+        x[4 * h + 1] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 1]) + bb.y, relu_lo), ss.y, oo.y);
+        x[4 * h + 2] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 2]) + bb.z, relu_lo), ss.z, oo.z);
+        x[4 * h + 3] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo), ss.w, oo.w);
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (col0 + i < n_cols) p[i] = __float2bfloat16_rn(v[i]);
+      if (OUT_BF16) {
+        mine[g] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                             pack_bf16x2(x[6], x[7]));
+      } else {
+        mine[2 * g] = make_uint4(__float_as_uint(x[0] + radd), __float_as_uint(x[1] + radd),
+                                 __float_as_uint(x[2] + radd), __float_as_uint(x[3] + radd));
+        mine[2 * g + 1] = make_uint4(__float_as_uint(x[4] + radd), __float_as_uint(x[5] + radd),
+                                     __float_as_uint(x[6] + radd), __float_as_uint(x[7] + radd));
+      }
     }
-  } else {
-    float* p = reinterpret_cast<float*>(out) + row * ld + col0;
-    if (col0 + 32 <= n_cols && ((reinterpret_cast<unsigned long long>(p) & 15ull) == 0)) {
+    __syncwarp();
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (col0 + i < n_cols) p[i] = v[i];
+    for (int j = 0; j < 4; ++j) {
+      const int q = j * 32 + lane, rr = q >> 2, part = q & 3;
+      const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kStgPitch + part * 16);
+      const int f = __shfl_sync(0xffffffffu, flags, rr);
+      unsigned char* dst = out0 + rr * ld_bytes + pass * 64 + part * 16;
+      if (f & kRowStore) {
+        *reinterpret_cast<uint4*>(dst) = v;
+        if (f & (kRowFirst | kRowLast)) {
+          const int lo = (f & kRowFirst) ? kHalo : 0, hi = (f & kRowLast) ? kHalo : 0;
+#pragma unroll 1
+          for (int h = -lo; h <= hi; ++h)
+            if (h != 0) *reinterpret_cast<uint4*>(dst + h * ld_bytes) = v;
+        }
+      }
     }
+    __syncwarp();
   }
 }
 
@@ -221,9 +251,10 @@ __device__ __forceinline__ void tile_coords(long long tile, long long m_tiles, i
 template <int MODE>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<unsigned long long>(smem_raw) + 1023ull) &
-                                                         ~1023ull);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // 1024-byte alignment for the 128B swizzle; offsetting the __shared__ array (instead of rounding a generic
+  // pointer) keeps the address space visible to the compiler, so the epilogue reads are LDS, not generic LD.
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + kStages * kABytes;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + kStages * kStageBytes);
@@ -234,6 +265,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty_bar + kAccStages);
   float* s_vec = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [kAccStages][3][BN]
   int* s_seg = reinterpret_cast<int*>(smem + kStages * kStageBytes + 256 + kVecBytes);  // [kAccStages][BN]
+  unsigned char* s_stg = smem + kStages * kStageBytes + 256 + kVecBytes + kSegBytes;    // [kEpiWarps][32][kStgPitch]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m_tiles = (a.m_rows + BM - 1) / BM;
@@ -329,6 +361,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;         // which 128 of the tile's 256 columns
     const int et = threadIdx.x - 64;          // 0..255
+    int staged_nt0 = -1, staged_nt1 = -1;     // n-tile whose epilogue vectors sit in s_vec[0] / s_vec[1]
     int it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       long long mt;
@@ -350,6 +383,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const bool unit_ok = row < a.m_rows;
         const float b = (unit_ok && a.bias) ? a.bias[row] : 0.0f;
+        const float relu_lo = a.relu ? 0.0f : -3.402823466e+38f;
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -375,8 +409,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (first != cur) { flush(); cur = first; s = 0.0f; s2 = 0.0f; }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float t = __uint_as_float(r[c & 1][i]) + b;
-              if (a.relu) t = fmaxf(t, 0.0f);
+              const float t = fmaxf(__uint_as_float(r[c & 1][i]) + b, relu_lo);
               s += t;
               s2 = fmaf(t, t, s2);
             }
@@ -386,8 +419,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int u = sc[i];
               if (u >= 0) {
                 if (u != cur) { flush(); cur = u; s = 0.0f; s2 = 0.0f; }
-                float t = __uint_as_float(r[c & 1][i]) + b;
-                if (a.relu) t = fmaxf(t, 0.0f);
+                const float t = fmaxf(__uint_as_float(r[c & 1][i]) + b, relu_lo);
                 s += t;
                 s2 = fmaf(t, t, s2);
               }
@@ -398,22 +430,37 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
         // ---- bias / ReLU / BatchNorm per column, rows stored as bf16 or fp32 ----
         float* vb = s_vec + acc * 3 * BN;
-        {
+        // The per-column vectors of an n-tile are staged once per accumulator stage and reused while the
+        // CTA keeps drawing the same n-tile (always, when gridDim.x is a multiple of n_tiles).
+        const int have_nt = acc ? staged_nt1 : staged_nt0;
+        if (have_nt != nt) {                                 // uniform over all epilogue threads
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");    // every warp is done reading the old vectors
           const int col = col_base + et;
           const bool ok = col < a.n_rows;
           vb[et] = (ok && a.bias) ? a.bias[col] : 0.0f;
           vb[BN + et] = (ok && a.scale) ? a.scale[col] : 1.0f;
           vb[2 * BN + et] = (ok && a.offset) ? a.offset[col] : 0.0f;
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+          if (acc) staged_nt1 = nt; else staged_nt0 = nt;
         }
         int flags = 0;
         if (row < a.m_rows) flags = a.rowmap ? a.rowmap[row] : kRowStore;
         float radd = 0.0f;
         if (MODE == kModeF32 && a.row_add != nullptr && row < a.m_rows) radd = a.row_add[row];
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
 
         const int n_cols = (int)a.n_rows;
+        constexpr bool kBf16 = (MODE == kModeBf16);
+        constexpr int kEs = kBf16 ? 2 : 4;                   // output element size
+        const long long ld_bytes = a.out_ld * kEs;
+        unsigned char* orow = reinterpret_cast<unsigned char*>(a.out) + row * ld_bytes;
+        unsigned char* owarp = reinterpret_cast<unsigned char*>(a.out) + (mt * BM + quarter * 32) * ld_bytes;
+        unsigned char* stg = s_stg + (warp - 2) * (32 * kStgPitch);
+        const bool vec_ok = ((reinterpret_cast<unsigned long long>(a.out) | (unsigned long long)ld_bytes) & 15ull) == 0;
+        const bool do_store = (flags & kRowStore) != 0;
+        const int halo_lo = (flags & kRowFirst) ? kHalo : 0, halo_hi = (flags & kRowLast) ? kHalo : 0;
+        const float relu_lo = a.relu ? 0.0f : -3.402823466e+38f;
         unsigned r[2][32];
         tmem_ld32_issue(taddr0, r[0]);
 #pragma unroll
@@ -421,37 +468,25 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_wait(r[c & 1]);
           if (c + 1 < 4) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) & 1]);
           const int cc = half * (BN / 2) + c * 32;        // column offset inside the tile
-          if (col_base + cc < n_cols) {                   // warp-uniform
-            float v[32];
-            const float4* b4 = reinterpret_cast<const float4*>(vb + cc);
-            const float4* s4 = reinterpret_cast<const float4*>(vb + BN + cc);
-            const float4* o4 = reinterpret_cast<const float4*>(vb + 2 * BN + cc);
+          const int col0 = col_base + cc;
+          if (col0 >= n_cols) continue;                   // warp-uniform
+          if (vec_ok && col0 + 32 <= n_cols) {
+            store_chunk<kBf16>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags,
+                               owarp + (long long)col0 * kEs, ld_bytes);
+          } else {
+            // ragged right edge (n_cols not a multiple of 32) or unaligned rows: element-wise stores
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 bb = b4[q], ss = s4[q], oo = o4[q];
-              float t0 = __uint_as_float(r[c & 1][4 * q + 0]) + bb.x;
-              float t1 = __uint_as_float(r[c & 1][4 * q + 1]) + bb.y;
-              float t2 = __uint_as_float(r[c & 1][4 * q + 2]) + bb.z;
-              float t3 = __uint_as_float(r[c & 1][4 * q + 3]) + bb.w;
-              if (a.relu) {
-                t0 = fmaxf(t0, 0.0f);
-                t1 = fmaxf(t1, 0.0f);
-                t2 = fmaxf(t2, 0.0f);
-                t3 = fmaxf(t3, 0.0f);
+            for (int i = 0; i < 32; ++i) {
+              float x = fmaxf(__uint_as_float(r[c & 1][i]) + vb[cc + i], relu_lo);
+              x = fmaf(x, vb[BN + cc + i], vb[2 * BN + cc + i]) + radd;
+              if (do_store && col0 + i < n_cols) {
+#pragma unroll 1
+                for (int h = -halo_lo; h <= halo_hi; ++h) {
+                  unsigned char* p = orow + h * ld_bytes + (long long)(col0 + i) * kEs;
+                  if (kBf16) *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(x);
+                  else *reinterpret_cast<float*>(p) = x;
+                }
               }
-              v[4 * q + 0] = fmaf(t0, ss.x, oo.x) + radd;
-              v[4 * q + 1] = fmaf(t1, ss.y, oo.y) + radd;
-              v[4 * q + 2] = fmaf(t2, ss.z, oo.z) + radd;
-              v[4 * q + 3] = fmaf(t3, ss.w, oo.w) + radd;
-            }
-            if (flags & kRowStore) {
-              store_row32<MODE == kModeBf16>(a.out, a.out_ld, row, col_base + cc, n_cols, v);
-              if (flags & kRowFirst)
-                for (int h = 1; h <= kHalo; ++h)
-                  store_row32<MODE == kModeBf16>(a.out, a.out_ld, row - h, col_base + cc, n_cols, v);
-              if (flags & kRowLast)
-                for (int h = 1; h <= kHalo; ++h)
-                  store_row32<MODE == kModeBf16>(a.out, a.out_ld, row + h, col_base + cc, n_cols, v);
             }
           }
         }
