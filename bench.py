@@ -2,26 +2,34 @@
 """
 bench.py -- headline benchmark of the wav -> x-vector hot path (BASELINE.json).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload frontend|wav2xvec|tdnn|plda]
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+                    [--workload frontend|wav2xvec|tdnn|plda] [--no-stages] [--no-cpu-baseline]
 
-N = 1 (default) measures BASELINE config 2, the configuration the metric is quoted on:
-  MFCC(30 mfcc / 30 mel) + CMVN(window 200) front-end on a batch of 1024 x 10 s of synthetic
-  16 kHz audio (float32, +-32767 scale).  One "step" = one pass of the hot path over one batch.
-N > 1 (launched under torchrun, one rank per GPU): the same per-GPU batch on every rank -- utterances
-  are sharded, there is NO data-path collective ("weak" scaling); value = all ranks' audio seconds /
-  max-over-ranks device time.
+Default workload (N = 1 and under torchrun): BASELINE config 2, the configuration the metric is quoted
+on -- MFCC(30 mfcc / 30 mel) + CMVN(window 200) on 1024 x 10 s of synthetic 16 kHz audio per GPU
+(float32, +-32767 scale).  One "step" = one pass of the hot path over one batch.  Utterances are sharded,
+there is NO data-path collective ("weak" scaling); value = all ranks' audio seconds / max-over-ranks
+device time.
 
-One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every field):
-  value      audio-seconds per second with the batch already resident in HBM (device-timed, CUDA events)
-  e2e        the same metric through the public layer API with HOST (pinned) buffers: H2D of the wav
-             batch and D2H of the features are inside the timed region every step
-  roofline   front-end kernel: algorithmic bytes (wav in + features out) / its own device time vs the
-             measured HBM peak in MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (oracle/ktf_oracle.py, an op-for-op NumPy port of the reference's layers;
-             the reference itself needs TensorFlow 2.8 which is not installable here) on a bounded sample
+One JSON line is printed by rank 0 (DESIGN.md section 6 explains every field):
+  value        audio-seconds per second with the batch already resident in HBM (CUDA events)
+  e2e          the same metric through the public layer API with HOST (pinned) buffers: H2D of the audio
+               and D2H of the result are inside the timed region every step
+  roofline     the dominant kernel: algorithmic bytes (or FLOPs) per launch / its own device time vs the
+               measured peak in MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (oracle/ktf_oracle.py, an op-for-op NumPy port of the reference's layers;
+               the reference itself needs TensorFlow 2.8, not installable here) on a bounded sample
+  stages       (N = 1, default workload only) the other BASELINE configs measured in the same run:
+               TDNN stack (config 3), full wav2xvec shard (config 4), PLDA scoring (config 5)
 
-`--impl reference` times that CPU port with all host threads on the same workload definition
-(a bounded sample per step); it is the only other place allowed to execute oracle/.
+Other workloads make one of those stages the headline line with the same schema:
+  wav2xvec     full pipeline with VAD + CMVN + TDNN(bf16) + LDA on gated-noise utterances (config 4 shard)
+  tdnn         SITW TDNN stack on 512 x 300 frames (config 3), roofline = tensor pipe
+  plda         all-vs-all PLDA scoring, enrolled columns sharded over the ranks, test vectors exchanged
+               with one NCCL all-gather (config 5); roofline = HBM writes of the fp32 scores
+
+`--impl reference` times the CPU port with all host threads on a bounded sample of the same workload
+(rank 0 only); it is the only other place allowed to execute oracle/.
 """
 
 import argparse
@@ -47,14 +55,20 @@ NUM_CEPS = 30
 CMVN_WINDOW = 200
 ALGO_BYTES_PER_UTT = UTT_SAMPLES * 4 + FRAMES * NUM_CEPS * 4      # wav once + features once
 
+TDNN_FLOP_PER_FRAME = 2 * (150 * 512 + 1536 * 512 + 1536 * 512 + 512 * 512 + 512 * 1500)   # 5 359 616
+TDNN_FLOP_PER_UTT = 2 * 3000 * 512                                                          # tdnn6
+PLDA_DIM = 128
 
-def measured_peaks():
+
+def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return {"hbm": float(d["hbm_gbs"]), "tf_burst": float(d["bf16_tflops"]),
+                "tf_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -72,7 +86,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -85,7 +99,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -107,207 +121,535 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU port (oracle) timing helpers -- cpu_baseline leg and --impl reference
+# shared model / data builders
 # ----------------------------------------------------------------------------------------------
 
-def synth_wav_np(n_utt, seed):
+def extractor_cfg():
+    import yaml
+    with open(os.path.join(ROOT, "data", "tflite_models", "0008_sitw_v2_1a.yml")) as f:
+        cfg = yaml.safe_load(f)["extractor"]
+    g = os.path.join(ROOT, "tests", "golden")
+    cfg["mfcc"]["dither"] = 0.0
+    cfg["xvec"]["model_config_path"] = os.path.join(ROOT, cfg["xvec"]["model_config_path"])
+    cfg["xvec"]["model_path"] = None                       # Kaldi final.raw is not vendored: seeded random init
+    cfg["xvec"]["global_mean_path"] = os.path.join(g, "sitw_mean.vec")
+    cfg["xvec"]["lda_matrix_path"] = os.path.join(g, "sitw_transform.mat")
+    return cfg
+
+
+def sitw_nnet_cfg():
+    import yaml
+    with open(os.path.join(ROOT, "data", "kaldi_models", "configs", "0008_sitw_v2_1a.yml")) as f:
+        return yaml.safe_load(f)["model_config"]
+
+
+def gated_noise_np(n_utt, seed):
+    """Gaussian noise (sigma 3000) gated by a random on/off envelope (0.2 s grain, ~70 %
+    duty), 'silence' sigma 30 -- so that the VAD keeps a non-trivial, threshold-robust subset."""
     rng = np.random.default_rng(seed)
-    return np.clip(rng.standard_normal((n_utt, UTT_SAMPLES), dtype=np.float32) * 3000.0, -32767, 32767)
+    x = rng.standard_normal((n_utt, UTT_SAMPLES), dtype=np.float32)
+    seg = 3200
+    on = (rng.random((n_utt, UTT_SAMPLES // seg)) < 0.7).astype(np.float32)
+    env = np.repeat(on, seg, axis=1)
+    return x * (30.0 + 2970.0 * env)
 
 
-def oracle_frontend(wav, chunk=8):
-    """The reference layers' arithmetic (NumPy port), a few utterances at a time to bound host memory."""
-    from oracle import ktf_oracle as O
-    outs = []
-    for i in range(0, wav.shape[0], chunk):
-        x = O.framing(wav[i:i + chunk], 25.0, 10.0, float(SR))
-        x = O.mfcc(x, num_mfccs=NUM_CEPS, num_mels=30)
-        outs.append(O.cmvn(x, window=CMVN_WINDOW))
-    return outs
+def gated_noise_cuda(n_utt, seed, dev):
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.randn((n_utt, UTT_SAMPLES), generator=g, device=dev)
+    seg = 3200
+    on = (torch.rand((n_utt, UTT_SAMPLES // seg), generator=g, device=dev) < 0.7).float()
+    return x * (30.0 + 2970.0 * on.repeat_interleave(seg, dim=1))
 
 
-def time_oracle(n_utt, threads, seed=0):
-    """Runs the NumPy port on n_utt utterances split over `threads` host threads; returns seconds."""
-    wav = synth_wav_np(n_utt, seed)
-    chunks = [c for c in np.array_split(np.arange(n_utt), threads) if len(c)]
+def synthetic_plda(dim, seed=1234):
+    rng = np.random.default_rng(seed)
+    psi = np.exp(np.linspace(3, -4, dim))
+    q, _ = np.linalg.qr(rng.standard_normal((dim, dim)))
+    Tm = q * rng.uniform(0.5, 2.0, size=(1, dim))
+    mean = rng.standard_normal(dim) * 0.05
+    return mean, Tm, psi
+
+
+def oracle_layers(seq):
+    import kaldi_tflite_b200 as ktf
+    out = []
+    for l in seq.layers:
+        if isinstance(l, ktf.layers.TDNN):
+            out.append({"type": "affine", "kernel": l.kernel, "bias": l.bias, "context": l.context})
+        elif isinstance(l, ktf.layers.ReLU):
+            out.append({"type": "relu"})
+        elif isinstance(l, ktf.layers.BatchNorm):
+            out.append({"type": "batchnorm", "gamma": l.gamma, "mean": l.moving_mean,
+                        "var": l.moving_variance, "epsilon": l.epsilon})
+        elif isinstance(l, ktf.layers.StatsPooling):
+            out.append({"type": "stats", "left_context": l.leftContext, "right_context": l.rightContext,
+                        "include_std": l.includeStd, "reduce_time_axis": l.reduce})
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU port (oracle) -- cpu_baseline leg and --impl reference.  The only code here that touches oracle/.
+# ----------------------------------------------------------------------------------------------
+
+def _threads_run(fn, items, threads):
+    chunks = [c for c in np.array_split(np.arange(len(items)), threads) if len(c)]
     t0 = time.perf_counter()
-    if len(chunks) == 1:
-        oracle_frontend(wav)
+    if len(chunks) <= 1:
+        fn(items)
     else:
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=len(chunks)) as ex:
-            list(ex.map(lambda idx: oracle_frontend(wav[idx]), chunks))
+            list(ex.map(lambda idx: fn(items[idx[0]:idx[-1] + 1]), chunks))
     return time.perf_counter() - t0
 
 
+class CpuPort:
+    """Bounded samples of each workload on the NumPy port of the reference layers."""
+
+    def __init__(self):
+        from oracle import ktf_oracle as O
+        self.O = O
+        self._wav2xvec = None
+
+    def frontend(self, n_utt, threads, seed=0):
+        O = self.O
+        rng = np.random.default_rng(seed)
+        wav = np.clip(rng.standard_normal((n_utt, UTT_SAMPLES), dtype=np.float32) * 3000.0, -32767, 32767)
+
+        def run(w):
+            for i in range(0, w.shape[0], 8):
+                x = O.framing(w[i:i + 8], 25.0, 10.0, float(SR))
+                x = O.mfcc(x, num_mfccs=NUM_CEPS, num_mels=30)
+                O.cmvn(x, window=CMVN_WINDOW)
+        return _threads_run(run, wav, threads), n_utt * UTT_SECONDS, "audio-s"
+
+    def _model(self):
+        if self._wav2xvec is None:
+            # weights come from the same seeded initialisers as the GPU arm; built WITHOUT touching CUDA
+            from kaldi_tflite_b200.models.sequential import SequentialFromConfig
+            from kaldi_tflite_b200.io import ReadKaldiArray
+            cfg = extractor_cfg()
+            seq = SequentialFromConfig(sitw_nnet_cfg(), None, "cmvn2xvec", seed=0)
+            seq._build_layers(30)
+            mean = np.ascontiguousarray(ReadKaldiArray(cfg["xvec"]["global_mean_path"], binary=True), np.float32)
+            lda = np.ascontiguousarray(ReadKaldiArray(cfg["xvec"]["lda_matrix_path"], binary=True), np.float32)
+            self._wav2xvec = (cfg, oracle_layers(seq), mean, lda)
+        return self._wav2xvec
+
+    def wav2xvec(self, n_utt, threads, seed=0):
+        O = self.O
+        cfg, layers, mean, lda = self._model()
+        wav = gated_noise_np(n_utt, seed)
+
+        def run(w):
+            for u in w:
+                O.xvector_extractor(u, cfg, layers, mean, lda)
+        return _threads_run(run, wav, threads), n_utt * UTT_SECONDS, "audio-s"
+
+    def tdnn(self, n_utt, threads, seed=0):
+        O = self.O
+        _, layers, _, _ = self._model()
+        x = np.random.default_rng(seed).standard_normal((n_utt, 300, 30)).astype(np.float32)
+
+        def run(xx):
+            for u in xx:
+                O.sequential(u[None], layers)
+        return _threads_run(run, x, threads), n_utt * 3.0, "audio-s"
+
+    def plda(self, n, threads, seed=0):
+        O = self.O
+        mean, Tm, psi = synthetic_plda(PLDA_DIM)
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal((n, PLDA_DIM))
+        x = (x / np.linalg.norm(x, axis=1, keepdims=True) * np.sqrt(PLDA_DIM)).astype(np.float32)
+        t0 = time.perf_counter()
+        O.plda(x, mean, Tm, psi, dtype=np.float32)           # the reference's (B, dim, B) broadcast formulation
+        return time.perf_counter() - t0, float(n) * n, "scores"
+
+
+CPU_SAMPLE = {"frontend": 192, "wav2xvec": 16, "tdnn": 32, "plda": 768}
+WORKLOAD_UNIT = {"frontend": "audio-s/s", "wav2xvec": "audio-s/s", "tdnn": "audio-s/s", "plda": "scores/s"}
+WORKLOAD_METRIC = {"frontend": "audio_sec_per_sec", "wav2xvec": "audio_sec_per_sec",
+                   "tdnn": "audio_sec_per_sec", "plda": "plda_scores_per_sec"}
+
+
+def cpu_baseline(workload, threads):
+    port = CpuPort()
+    n = CPU_SAMPLE[workload] * (max(1, threads // 2) if workload != "plda" else 1)
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=1 if threads == 1 else None)
+    except ImportError:
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        secs, units, what = getattr(port, workload)(n, threads)
+    desc = {"frontend": f"{n} utterances x {UTT_SECONDS} s of the same MFCC+CMVN workload",
+            "wav2xvec": f"{n} gated-noise utterances x {UTT_SECONDS} s through the whole pipeline",
+            "tdnn": f"{n} x 300-frame chunks through the SITW stack (fp32)",
+            "plda": f"{n} x {n} trials, (B, dim, B) broadcast formulation of the reference (fp32)"}[workload]
+    return {"value": units / secs, "unit": WORKLOAD_UNIT[workload], "cores": threads, "kind": "port",
+            "sample": f"{desc}; NumPy port of the reference layers (TensorFlow unavailable), {secs:.1f} s"}
+
+
+def workload_config(workload, n_gpus):
+    base = {"parallelism": f"utterance-sharded x{n_gpus}, no collective"}
+    if workload == "frontend":
+        base.update({"workload": "BASELINE config 2: Framing(25ms/10ms) -> MFCC(30 mfcc, 30 mel, povey, dither 0) -> "
+                                 "CMVN(window 200), batch 1024 x 10 s synthetic 16 kHz float32 audio per GPU",
+                     "batch_per_gpu": BATCH, "utt_seconds": UTT_SECONDS, "frames_per_utt": FRAMES,
+                     "l2_policy": "input batch is 655 MB per step, larger than the 126 MB L2 (no explicit flush needed)"})
+    elif workload == "wav2xvec":
+        base.update({"workload": "BASELINE config 4 shard: full wav2xvec (MFCC -> VAD mask -> CMVN(300) -> SITW TDNN "
+                                 "bf16 -> stats -> LDA/length-norm), 1024 gated-noise utterances x 10 s per GPU, "
+                                 "random-init TDNN (Kaldi weights not vendored), real LDA / mean",
+                     "batch_per_gpu": BATCH, "utt_seconds": UTT_SECONDS, "tdnn_precision": "bf16 operands, fp32 accumulate",
+                     "l2_policy": "655 MB of audio and > 1 GB of activations per step, larger than the 126 MB L2"})
+    elif workload == "tdnn":
+        base.update({"workload": "BASELINE config 3: SITW x-vector TDNN (5 TDNN-512 + 1500-d stats + 512 embedding, "
+                                 "random init), batch 512 x 300 frames per GPU",
+                     "batch_per_gpu": 512, "frames_per_utt": 300, "tdnn_precision": "bf16 operands, fp32 accumulate",
+                     "l2_policy": "L2 flushed between timed iterations (256 MB scratch write)"})
+    else:
+        base.update({"workload": "BASELINE config 5: PLDA all-vs-all 50k enroll x 50k test x-vectors (dim 128), enrolled "
+                                 "columns sharded over the ranks, test vectors exchanged with one all-gather",
+                     "parallelism": f"enrolled columns sharded x{n_gpus}, NCCL all-gather of the transformed test vectors",
+                     "n_enroll": 50000, "n_test": 50000, "dim": PLDA_DIM,
+                     "l2_policy": "each step writes >= 1.25 GB of scores per GPU, larger than the 126 MB L2"})
+    return base
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm
+# ----------------------------------------------------------------------------------------------
+
 def run_reference(args):
-    """Reference arm: the CPU port of the reference's layers on all host threads (TensorFlow 2.8, which the
-    reference needs, is not installable in this image: `import tensorflow` fails, no network)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """The CPU port of the reference's layers on all host threads (TensorFlow 2.8, which the reference
+    needs, is not installable in this image: `import tensorflow` fails, no network)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
-    n_utt = max(threads, 32)                         # bounded sample of the 1024-utterance batch per step
+    port = CpuPort()
+    w = args.workload
+    n = CPU_SAMPLE[w] * (max(1, threads // 2) if w != "plda" else 1)
+    if w != "frontend":
+        n = max(n // 4, threads if w != "plda" else 256)      # keep K + W steps within a few minutes
     for _ in range(args.warmup):
-        time_oracle(n_utt, threads)
-    t = 0.0
+        getattr(port, w)(n, threads)
+    t, units = 0.0, 0.0
     for s in range(args.steps):
-        t += time_oracle(n_utt, threads, seed=s)
-    value = n_utt * UTT_SECONDS * args.steps / t
+        secs, u, _ = getattr(port, w)(n, threads, seed=s)
+        t += secs
+        units += u
+    value = units / t
     line = {
-        "impl": "reference", "metric": "audio_sec_per_sec", "value": value, "unit": "audio-s/s",
+        "impl": "reference", "metric": WORKLOAD_METRIC[w], "value": value, "unit": WORKLOAD_UNIT[w],
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t / args.steps * (BATCH / n_utt), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_utt} of {BATCH} utterances x {UTT_SECONDS} s per step "
-                                   f"(NumPy port of the reference layers; TensorFlow unavailable)"},
-        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(w, args.gpus),
+        "cpu_baseline": {"value": value, "unit": WORKLOAD_UNIT[w], "cores": threads, "kind": "port",
+                         "sample": f"{n} units of the workload per step (NumPy port of the reference layers; "
+                                   f"TensorFlow unavailable)"},
+        "e2e": {"value": value, "unit": WORKLOAD_UNIT[w], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
-
-
-def workload_config(n_gpus):
-    return {"workload": "BASELINE config 2: Framing(25ms/10ms) -> MFCC(30 mfcc, 30 mel, povey, dither 0) -> "
-                        "CMVN(window 200), batch 1024 x 10 s synthetic 16 kHz float32 audio per GPU",
-            "batch_per_gpu": BATCH, "utt_seconds": UTT_SECONDS, "frames_per_utt": FRAMES,
-            "parallelism": f"utterance-sharded x{n_gpus}, no collective",
-            "l2_policy": "input batch is 655 MB per step, larger than the 126 MB L2 (no explicit flush needed)"}
 
 
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Harness:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference "
+                             "for the CPU port")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.args = args
+        self.flush_buf = None
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU port")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
+    def flush_l2(self):
+        if self.flush_buf is None:
+            self.flush_buf = self.torch.empty(64 * 1024 * 1024, dtype=self.torch.float32, device=self.dev)
+        self.flush_buf.fill_(1.0)
+
+    def max_over_ranks(self, ms):
+        t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, step, steps, warmup, flush=False, inner=None):
+        """W warm-up steps, then K steps bracketed by barrier + synchronize; returns (ms total [max over
+        ranks], launches, clocks, mean ms of the `inner` event pairs recorded by step())."""
+        import kaldi_tflite_b200 as ktf
+        torch = self.torch
+        for _ in range(max(warmup, 3)):
+            step(None)
+        self.barrier()
+        sampler = ClockSampler(self.local_rank)
+        sampler.start()
+        pairs = []
+        n0 = ktf.launch_count()
+        self.barrier()
+        if flush:
+            # per-step events so that the L2 flush writes stay outside the measured time
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for s in range(steps):
+                self.flush_l2()
+                evs[s][0].record()
+                step(pairs)
+                evs[s][1].record()
+            self.barrier()
+            ms = sum(a.elapsed_time(b) for a, b in evs)
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for s in range(steps):
+                step(pairs)
+            e1.record()
+            self.barrier()
+            ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        launches = ktf.launch_count() - n0
+        inner_ms = float(np.mean([a.elapsed_time(b) for a, b in pairs])) if pairs else None
+        return self.max_over_ranks(ms), int(launches), clocks, inner_ms
+
+
+def ev_pair(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def stage_tdnn(h, steps, warmup):
     import kaldi_tflite_b200 as ktf
-    from kaldi_tflite_b200 import _native, _tensor
+    torch = h.torch
+    mdl = ktf.models.SequentialFromConfig(sitw_nnet_cfg(), None, "cmvn2xvec", precision="bf16", seed=0)
+    g = torch.Generator(device=h.dev).manual_seed(1234 + h.rank)
+    B, Tn = 512, 300
+    feats = torch.randn((B * Tn, 30), generator=g, device=h.dev)
+    offs = torch.arange(B + 1, device=h.dev, dtype=torch.int64) * Tn
 
-    dev = torch.device("cuda", local_rank)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    wav = (torch.randn((BATCH, UTT_SAMPLES), generator=g, device=dev) * 3000.0).clamp_(-32767, 32767)
+    def step(pairs):
+        mdl.forward_ragged(feats, offs)
+    ms, launches, clocks, _ = h.timed(step, steps, warmup, flush=True)
+    flops = (TDNN_FLOP_PER_FRAME * B * Tn + TDNN_FLOP_PER_UTT * B) * steps
+    host_in = torch.empty((B * Tn, 30), dtype=torch.float32, pin_memory=True).copy_(feats)
+    host_out = torch.empty((B, 512), dtype=torch.float32, pin_memory=True)
 
+    def e2e(pairs):
+        y, _ = mdl.forward_ragged(host_in.to(h.dev, non_blocking=True), offs)
+        host_out.copy_(y, non_blocking=True)
+    ms_e2e, _, _, _ = h.timed(e2e, steps, 2)
+    return {"ms": ms, "steps": steps, "launches": launches, "clocks": clocks, "units": B * 3.0 * h.world * steps,
+            "flops": flops, "ms_e2e": ms_e2e, "h2d": B * Tn * 30 * 4, "d2h": B * 512 * 4}
+
+
+def stage_wav2xvec(h, steps, warmup, batch=BATCH):
+    import kaldi_tflite_b200 as ktf
+    torch = h.torch
+    ext = ktf.models.XvectorExtractor(extractor_cfg(), precision="bf16", seed=0)
+    wav = gated_noise_cuda(batch, 7 + h.rank, h.dev)
+    _, inter = ext(wav, return_intermediate=True)
+    kept = int(inter["voiced_offsets"][-1].item())
+
+    def step(pairs):
+        if pairs is None:
+            ext(wav)
+            return
+        feats, offsets = ext.features(*ext._flatten(wav))
+        mask = ext.vad.mask_ragged(feats, offsets)
+        voiced, voffs, _ = ext.vad.compact_ragged(feats, mask, offsets, gather=True)
+        normed, _ = ext.cmvn.forward_ragged(voiced, voffs, max_frames=FRAMES)
+        a, b = ev_pair(torch)
+        a.record()
+        emb, _ = ext.xvec.forward_ragged(normed, voffs)     # the TDNN stack: 7 tcgen05 GEMM launches
+        b.record()
+        pairs.append((a, b))
+        ext.backend(emb)
+    ms, launches, clocks, tdnn_ms = h.timed(step, steps, warmup)
+    host_in = torch.empty((batch, UTT_SAMPLES), dtype=torch.float32, pin_memory=True).copy_(wav)
+    host_out = torch.empty((batch, 128), dtype=torch.float32, pin_memory=True)
+
+    def e2e(pairs):
+        host_out.copy_(ext(host_in.to(h.dev, non_blocking=True)), non_blocking=True)   # public API call
+    ms_e2e, _, _, _ = h.timed(e2e, steps, 2)
+    return {"ms": ms, "steps": steps, "launches": launches, "clocks": clocks,
+            "units": batch * UTT_SECONDS * h.world * steps, "tdnn_ms": tdnn_ms,
+            "flops": TDNN_FLOP_PER_FRAME * kept + TDNN_FLOP_PER_UTT * batch, "vad_keep": kept / (batch * FRAMES),
+            "ms_e2e": ms_e2e, "h2d": batch * UTT_SAMPLES * 4, "d2h": batch * 128 * 4}
+
+
+def stage_plda(h, steps, warmup, n=50000):
+    import kaldi_tflite_b200 as ktf
+    from kaldi_tflite_b200 import parallel
+    torch = h.torch
+    mean, Tm, psi = synthetic_plda(PLDA_DIM)
+    layer = ktf.layers.PLDA(PLDA_DIM, mean, Tm, psi, dtype=np.float32, return_transformed=False)
+    g = torch.Generator(device=h.dev).manual_seed(1234 + h.rank)
+    lo, hi = parallel.shard_range(n, h.rank, h.world)
+
+    def xvecs(count):
+        x = torch.randn((count, PLDA_DIM), generator=g, device=h.dev)
+        return x / x.norm(dim=1, keepdim=True) * PLDA_DIM ** 0.5
+    x_test, x_enroll = xvecs(hi - lo), xvecs(hi - lo)
+    scores = torch.empty((n, hi - lo), device=h.dev, dtype=torch.float32)
+
+    def step(pairs):
+        a, b = ev_pair(torch)
+        u_test = layer.transformVector(x_test)
+        u_enroll = layer.transformVector(x_enroll)
+        u_all = parallel.gather_rows(u_test)                 # the only collective: NCCL all-gather (25.6 MB total)
+        if pairs is not None:
+            a.record()
+        layer.logLikelihoodRatio(u_all, u_enroll, out=scores)
+        if pairs is not None:
+            b.record()
+            pairs.append((a, b))
+    ms, launches, clocks, score_ms = h.timed(step, steps, warmup)
+    host_t = torch.empty_like(x_test, device="cpu").pin_memory().copy_(x_test)
+    host_e = torch.empty_like(x_enroll, device="cpu").pin_memory().copy_(x_enroll)
+    host_top = torch.empty((n,), dtype=torch.float32, pin_memory=True)
+
+    def e2e(pairs):
+        ut = layer.transformVector(host_t.to(h.dev, non_blocking=True))
+        ue = layer.transformVector(host_e.to(h.dev, non_blocking=True))
+        layer.logLikelihoodRatio(parallel.gather_rows(ut), ue, out=scores)
+        host_top.copy_(scores.max(dim=1).values, non_blocking=True)    # result read back: best trial per test vector
+    ms_e2e, _, _, _ = h.timed(e2e, steps, 2)
+    return {"ms": ms, "steps": steps, "launches": launches, "clocks": clocks, "units": float(n) * n * steps,
+            "score_ms": score_ms, "score_bytes": float(n) * (hi - lo) * 4, "flops": 2.0 * n * (hi - lo) * PLDA_DIM,
+            "ms_e2e": ms_e2e, "h2d": 2 * (hi - lo) * PLDA_DIM * 4, "d2h": n * 4}
+
+
+def stage_frontend(h, steps, warmup):
+    import kaldi_tflite_b200 as ktf
+    torch = h.torch
+    g = torch.Generator(device=h.dev).manual_seed(1234 + h.rank)
+    wav = (torch.randn((BATCH, UTT_SAMPLES), generator=g, device=h.dev) * 3000.0).clamp_(-32767, 32767)
     framing = ktf.layers.Framing(25.0, 10.0, float(SR), dynamic_input_shape=True)
     mfcc = ktf.layers.MFCC(num_mfccs=NUM_CEPS, num_mels=30)
     cmvn = ktf.layers.CMVN(center=True, window=CMVN_WINDOW, norm_vars=False)
-
-    def step(x):
-        return cmvn(mfcc(framing(x)))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        out = step(wav)
-    barrier()
-
-    # ---- device-resident timing (value) + per-kernel timing of the front-end kernel (roofline) ----
     fe = mfcc.frontend(framing.frameWidth, framing.frameShift)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    n0 = ktf.launch_count()
-    sampler.start()
-    barrier()
-    ev0.record()
-    for s in range(args.steps):
-        k_ev[s][0].record()
-        feats, _ = fe.forward(wav)                         # the fused front-end kernel (one launch)
-        k_ev[s][1].record()
-        out = cmvn(feats)
-    ev1.record()
-    barrier()
-    clocks = sampler.stop()
-    launches = ktf.launch_count() - n0
-    ms_total = ev0.elapsed_time(ev1)
-    ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
 
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
-
-    # ---- end-to-end through the public API with host buffers ---------------------------------------
-    host_in = torch.empty((BATCH, UTT_SAMPLES), dtype=torch.float32, pin_memory=True)
-    host_in.copy_(wav)
+    def step(pairs):
+        if pairs is None:
+            cmvn(mfcc(framing(wav)))
+            return
+        a, b = ev_pair(torch)
+        a.record()
+        feats, _ = fe.forward(wav)                           # the fused front-end kernel (one launch)
+        b.record()
+        pairs.append((a, b))
+        cmvn(feats)
+    ms, launches, clocks, k_ms = h.timed(step, steps, warmup)
+    host_in = torch.empty((BATCH, UTT_SAMPLES), dtype=torch.float32, pin_memory=True).copy_(wav)
     host_out = torch.empty((BATCH, FRAMES, NUM_CEPS), dtype=torch.float32, pin_memory=True)
-    for _ in range(2):
-        host_out.copy_(step(host_in.to(dev, non_blocking=True)), non_blocking=True)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        x = host_in.to(dev, non_blocking=True)              # H2D of this step's inputs
-        y = step(x)                                         # public layer API
-        host_out.copy_(y, non_blocking=True)                # D2H of this step's result
-    e1.record()
-    barrier()
-    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    ms_e2e_max = float(t2.item())
 
-    if rank == 0:
-        audio_s = BATCH * UTT_SECONDS * world * args.steps
-        peak, peak_src = measured_peaks()
-        achieved = ALGO_BYTES_PER_UTT * BATCH / (ms_kernel * 1e-3) / 1e9
-        # bounded CPU-port sample on rank 0 (N = 1 only): 1 thread, 192 utterances ~ 10-20 s
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            n_cpu = 192
-            try:                                            # keep BLAS / FFT pools at one thread
-                from threadpoolctl import threadpool_limits
-                with threadpool_limits(limits=1):
-                    tc = time_oracle(n_cpu, 1)
-            except ImportError:
-                tc = time_oracle(n_cpu, 1)
-            cpu = {"value": n_cpu * UTT_SECONDS / tc, "unit": "audio-s/s", "cores": 1, "kind": "port",
-                   "sample": f"{n_cpu} utterances x {UTT_SECONDS} s of the same workload, NumPy port of the "
-                             f"reference layers, 1 thread ({tc:.1f} s)"}
+    def e2e(pairs):
+        host_out.copy_(cmvn(mfcc(framing(host_in.to(h.dev, non_blocking=True)))), non_blocking=True)
+    ms_e2e, _, _, _ = h.timed(e2e, steps, 2)
+    return {"ms": ms, "steps": steps, "launches": launches, "clocks": clocks,
+            "units": BATCH * UTT_SECONDS * h.world * steps, "kernel_ms": k_ms,
+            "ms_e2e": ms_e2e, "h2d": BATCH * UTT_SAMPLES * 4, "d2h": BATCH * FRAMES * NUM_CEPS * 4}
+
+
+def roofline_for(workload, r, pk):
+    if workload == "frontend":
+        achieved = ALGO_BYTES_PER_UTT * BATCH / (r["kernel_ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+                "traffic": None, "peak_source": pk["src"] + " hbm_gbs",
+                "kernel": "frontend_kernel (framing+window+FFT+mel+log+DCT)", "kernel_ms": r["kernel_ms"],
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UTT * BATCH}
+        tf = os.path.join(ROOT, "profiles", "frontend_traffic.json")
+        if os.path.exists(tf):
+            with open(tf) as f:
+                roof["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        return roof
+    if workload in ("tdnn", "wav2xvec"):
+        ms = r["ms"] / r["steps"] if workload == "tdnn" else r["tdnn_ms"]
+        flops = r["flops"] / r["steps"] if workload == "tdnn" else r["flops"]
+        achieved = flops / (ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tf_sustained"], "frac_of_burst": achieved / pk["tf_burst"], "traffic": None,
+                "peak_source": pk["src"] + " bf16_tflops_sustained (kernels timed inside a long step)",
+                "kernel": "tdnn_tc_kernel x7 (tcgen05 implicit-GEMM stack incl. splice / finalize launches)",
+                "kernel_ms": ms, "algorithmic_flops_per_launch": flops}
+    achieved = r["score_bytes"] / (r["score_ms"] * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+            "traffic": None, "peak_source": pk["src"] + " hbm_gbs",
+            "kernel": "tdnn_tc_kernel<F32> as PLDA score GEMM (fp16 hi/lo split, K = 3*dim) + split / A_i / B_j kernels",
+            "kernel_ms": r["score_ms"], "algorithmic_bytes_per_launch": r["score_bytes"],
+            "tensor_tflops": r["flops"] * 3 / (r["score_ms"] * 1e-3) / 1e12}
+
+
+STAGES = {"frontend": stage_frontend, "wav2xvec": stage_wav2xvec, "tdnn": stage_tdnn, "plda": stage_plda}
+
+
+def run_ours(args):
+    h = Harness(args)
+    pk = peaks()
+    w = args.workload
+    r = STAGES[w](h, args.steps, args.warmup)
+    line = None
+    if h.rank == 0:
         line = {
-            "metric": "audio_sec_per_sec", "value": audio_s / (ms_total_max * 1e-3), "unit": "audio-s/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "frontend_kernel<32,25> (framing+window+FFT+mel+log+DCT)",
-                         "kernel_ms": ms_kernel,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UTT * BATCH},
-            "e2e": {"value": audio_s / (ms_e2e_max * 1e-3), "unit": "audio-s/s",
-                    "h2d_bytes_per_step": BATCH * UTT_SAMPLES * 4,
-                    "d2h_bytes_per_step": BATCH * FRAMES * NUM_CEPS * 4,
-                    "ms_per_step": ms_e2e_max / args.steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+            "metric": WORKLOAD_METRIC[w], "value": r["units"] / (r["ms"] * 1e-3), "unit": WORKLOAD_UNIT[w],
+            "n_gpus": h.world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": r["ms"] / args.steps, "higher_is_better": True,
+            "scaling": "strong" if w == "plda" else "weak",
+            "vs_baseline": None, "dtype": {"frontend": "f32", "plda": "f32 (fp16 hi/lo split products, fp32 accumulate)"}.get(
+                w, "bf16 operands, fp32 accumulate"),
+            "data": "synthetic", "config": workload_config(w, h.world),
+            "roofline": roofline_for(w, r, pk),
+            "e2e": {"value": r["units"] / (r["ms_e2e"] * 1e-3), "unit": WORKLOAD_UNIT[w],
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["ms_e2e"] / args.steps},
+            "gpu_launches": r["launches"], "clocks": r["clocks"],
         }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
-        traffic_file = os.path.join(ROOT, "profiles", "frontend_traffic.json")
-        if os.path.exists(traffic_file):
-            with open(traffic_file) as f:
-                line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        if "vad_keep" in r:
+            line["config"]["vad_keep_fraction"] = r["vad_keep"]
+    # the other configs, measured in the same run (N = 1, default workload only)
+    if w == "frontend" and h.world == 1 and not args.no_stages:
+        stages = {}
+        for name, kw in (("tdnn", {}), ("wav2xvec", {}), ("plda", {"n": 32768})):
+            try:
+                s = STAGES[name](h, max(3, args.steps // 4), 3, **kw)
+                roof = roofline_for(name, s, pk)
+                stages[name] = {"value": s["units"] / (s["ms"] * 1e-3), "unit": WORKLOAD_UNIT[name],
+                                "ms_per_step": s["ms"] / s["steps"], "launches_per_step": s["launches"] // s["steps"],
+                                "e2e_value": s["units"] / (s["ms_e2e"] * 1e-3),
+                                "roofline": {k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms")}}
+                if name == "plda":
+                    stages[name]["n"] = kw["n"]
+                if "vad_keep" in s:
+                    stages[name]["vad_keep_fraction"] = s["vad_keep"]
+            except Exception as e:                              # a stage must never take the headline line down
+                stages[name] = {"error": f"{type(e).__name__}: {e}"}
+        line["stages"] = stages
+    if h.rank == 0:
+        if h.world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(w, 1)           # bounded sample, 1 thread, rank 0, N = 1 only
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if h.world > 1:
+        h.dist.destroy_process_group()
 
 
 def main():
@@ -316,7 +658,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="frontend", choices=sorted(STAGES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -15,8 +15,9 @@
 //     kHalo replicated rows on both sides ("padded rows"); the epilogue of each layer writes the halo
 //     replicas the next layer's taps need and skips the halo rows of its own tile;
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
-//     warps 2..9 = epilogue (two warps per TMEM lane quarter, each owning half of the tile's columns;
-//     TMEM loads are software-pipelined against the bias/ReLU/BN math and the global stores);
+//     warps 2..9 = epilogue (two warps per TMEM lane quarter, each owning 128 of the tile's columns; TMEM
+//     loads run one chunk ahead; rows are transposed through a per-warp smem buffer so that global stores
+//     cover full 32-byte sectors, 64 contiguous bytes per row);
 //   * 4-stage smem ring (48 KB per stage) between TMA and MMA, 2 accumulator stages of 256 TMEM columns
 //     between MMA and epilogue, persistent CTAs (one per SM);
 //   * three epilogues: bf16 rows (next layer's operand), fp32 rows (+ per-row / per-column addends:
@@ -27,6 +28,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -40,16 +43,19 @@ constexpr int kHalo = 4;          // replicated rows on each side of every utter
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 8;                         // 2 per TMEM lane quarter, 128 tile columns each
 constexpr int kEpiThreads = kEpiWarps * 32;          // 256
 constexpr int kThreadsTc = 64 + kEpiThreads;         // 10 warps
+constexpr int kEpiCols = BN / (kEpiWarps / 4);       // 64 columns of the tile per epilogue warp
+constexpr int kEpiChunks = kEpiCols / 32;            // 32-column TMEM loads per warp and tile
 constexpr int kABytes = BM * BK * 2;                 // 16 KB
 constexpr int kBBytes = BN * BK * 2;                 // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kVecBytes = kAccStages * 3 * BN * 4;   // epilogue vectors (bias / scale / offset)
 constexpr int kSegBytes = kAccStages * BN * 4;       // STATS: utterance id of every frame of the tile
-constexpr int kStgPitch = 80;                        // bytes per staged row: 64 B payload + 16 B (bank spread)
-constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch;  // per-warp 32 x 64 B transpose buffers for coalesced stores
+constexpr int kRowSeg = 64;                          // bytes of one output row written by one group of lanes
+constexpr int kStgPitch = kRowSeg + 16;              // staged row pitch: payload + 16 B (bank spread)
+constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch;  // per-warp 32-row transpose buffers for coalesced stores
 constexpr int kSmemTc = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kVecBytes + kSegBytes + kStgBytes;
 
 enum { kModeBf16 = 0, kModeF32 = 1, kModeStats = 2 };
@@ -76,6 +82,11 @@ struct TcArgs {
   void* out;                // bf16 or fp32, row-major
   long long out_ld;
   float* sums;              // STATS: (batch, 2, m_rows) raw sum / sum of squares of relu(acc + bias)
+  const void* act_base;     // activation matrix (the operand that streams from HBM), for the L2 prefetch
+  long long act_ld_bytes;   // its row pitch and row count
+  long long act_rows;
+  int reverse;              // walk the tiles from the last row block to the first (see launch_gemm)
+  int debug;                // development knobs (KTF_TC_DEBUG): 1 = skip global stores, 2 = skip the epilogue math
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -115,6 +126,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           "r"(smem_u32(smem_dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// Pulls a contiguous byte range into L2 (no smem, no barrier).  The smem ring holds 4 k-blocks (~1 us of
+// MMA work), less than the HBM latency under load, so the activation rows of a CTA's NEXT tile are
+// requested one whole tile ahead with a single bulk prefetch.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // K-major, 128B-swizzled operand tile: rows of 64 16-bit elements (128 B), 8-row groups 1024 B apart.
@@ -177,23 +195,28 @@ __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
 // A thread owns one ROW of the accumulator (TMEM lane), so storing straight from registers would make every
 // warp-wide store touch 32 different rows with 16 bytes each (32 partial sectors per instruction -- measured
 // as the bottleneck of the K <= 512 layers).  The chunk is therefore transposed through a per-warp staging
-// buffer in 64-byte row segments (32 bf16 / 16 fp32 columns): lanes write their own row, then 4 consecutive
-// lanes read back one row segment, so a warp store covers 8 rows x 64 contiguous bytes (16 full sectors).
+// buffer in kRowSeg-byte row segments (32 bf16 / 16 fp32 columns): lanes write their own row, then 4
+// consecutive lanes read back one row segment, so a warp store covers 8 rows x 64 contiguous bytes (16 full
+// sectors).
 // Rows flagged first / last also write their kHalo replicas; rows without kRowStore are skipped.
-template <bool OUT_BF16>
+// VEC = false (ragged right edge, unaligned output): fp32 staging, bounds-checked scalar stores.
+template <bool OUT_BF16, bool VEC>
 __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float* vb, float relu_lo, float radd,
                                             unsigned char* stg, int lane, int flags, unsigned char* out0,
-                                            long long ld_bytes) {
+                                            long long ld_bytes, int cols_left) {
   const float4* b4 = reinterpret_cast<const float4*>(vb);
   const float4* s4 = reinterpret_cast<const float4*>(vb + BN);
   const float4* o4 = reinterpret_cast<const float4*>(vb + 2 * BN);
-  constexpr int kPasses = OUT_BF16 ? 1 : 2;     // 64-byte segments per 32-column chunk
+  constexpr bool kPacked = OUT_BF16 && VEC;        // staged as bf16 or as fp32
+  constexpr int kCols = kRowSeg / (kPacked ? 2 : 4);   // columns per staged row segment
+  constexpr int kPieces = kRowSeg / 16;            // 16-byte pieces per row segment
+  constexpr int kEs = OUT_BF16 ? 2 : 4;
 #pragma unroll
-  for (int pass = 0; pass < kPasses; ++pass) {
+  for (int pass = 0; pass < 32 / kCols; ++pass) {
     uint4* mine = reinterpret_cast<uint4*>(stg + lane * kStgPitch);
 #pragma unroll
-    for (int g = 0; g < (OUT_BF16 ? 4 : 2); ++g) {      // 8 columns per group
-      const int c8 = OUT_BF16 ? g : 2 * pass + g;       // which group of 8 columns of the chunk
+    for (int g = 0; g < kCols / 8; ++g) {          // 8 columns per group
+      const int c8 = pass * (kCols / 8) + g;       // which group of 8 columns of the chunk
       float x[8];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -203,7 +226,7 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
         x[4 * h + 2] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 2]) + bb.z, relu_lo), ss.z, oo.z);
         x[4 * h + 3] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo), ss.w, oo.w);
       }
-      if (OUT_BF16) {
+      if (kPacked) {
         mine[g] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
                              pack_bf16x2(x[6], x[7]));
       } else {
@@ -214,19 +237,37 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
       }
     }
     __syncwarp();
+    if (VEC) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int q = j * 32 + lane, rr = q >> 2, part = q & 3;
-      const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kStgPitch + part * 16);
-      const int f = __shfl_sync(0xffffffffu, flags, rr);
-      unsigned char* dst = out0 + rr * ld_bytes + pass * 64 + part * 16;
-      if (f & kRowStore) {
-        *reinterpret_cast<uint4*>(dst) = v;
-        if (f & (kRowFirst | kRowLast)) {
-          const int lo = (f & kRowFirst) ? kHalo : 0, hi = (f & kRowLast) ? kHalo : 0;
+      for (int j = 0; j < kPieces; ++j) {
+        const int q = j * 32 + lane, rr = q / kPieces, part = q % kPieces;
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kStgPitch + part * 16);
+        const int f = __shfl_sync(0xffffffffu, flags, rr);
+        unsigned char* dst = out0 + rr * ld_bytes + pass * kRowSeg + part * 16;
+        if (f & kRowStore) {
+          *reinterpret_cast<uint4*>(dst) = v;
+          if (f & (kRowFirst | kRowLast)) {
+            const int lo = (f & kRowFirst) ? kHalo : 0, hi = (f & kRowLast) ? kHalo : 0;
 #pragma unroll 1
-          for (int h = -lo; h <= hi; ++h)
-            if (h != 0) *reinterpret_cast<uint4*>(dst + h * ld_bytes) = v;
+            for (int h = -lo; h <= hi; ++h)
+              if (h != 0) *reinterpret_cast<uint4*>(dst + h * ld_bytes) = v;
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int k = lane; k < 32 * kCols; k += 32) {
+        const int rr = k / kCols, col = k % kCols;
+        const float v = *reinterpret_cast<const float*>(stg + rr * kStgPitch + col * 4);
+        const int f = __shfl_sync(0xffffffffu, flags, rr);
+        if ((f & kRowStore) && pass * kCols + col < cols_left) {
+          const int lo = (f & kRowFirst) ? kHalo : 0, hi = (f & kRowLast) ? kHalo : 0;
+          unsigned char* dst = out0 + rr * ld_bytes + (long long)(pass * kCols + col) * kEs;
+#pragma unroll 1
+          for (int h = -lo; h <= hi; ++h) {
+            if (OUT_BF16) *reinterpret_cast<__nv_bfloat16*>(dst + h * ld_bytes) = __float2bfloat16_rn(v);
+            else *reinterpret_cast<float*>(dst + h * ld_bytes) = v;
+          }
         }
       }
     }
@@ -237,7 +278,9 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
 // Tile walk: row-storing modes go n-fastest (the n-tiles of one row block run on neighbouring CTAs and
 // share the activation rows through L2); STATS goes m-fastest (the unit tiles of one frame block).
 template <int MODE>
-__device__ __forceinline__ void tile_coords(long long tile, long long m_tiles, int n_tiles, long long& mt, int& nt) {
+__device__ __forceinline__ void tile_coords(long long tile, long long m_tiles, int n_tiles, int reverse, long long& mt,
+                                            int& nt) {
+  if (reverse) tile = m_tiles * n_tiles - 1 - tile;
   if (MODE == kModeStats) {
     const long long q = tile / m_tiles;
     mt = tile - q * m_tiles;
@@ -304,8 +347,25 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         long long mt;
         int nt;
-        tile_coords<MODE>(tile, m_tiles, n_tiles, mt, nt);
+        tile_coords<MODE>(tile, m_tiles, n_tiles, a.reverse, mt, nt);
         const int m0 = (int)(mt * BM), n0 = nt * BN;
+        if (a.act_base != nullptr && tile + gridDim.x < total_tiles) {
+          long long mt2;
+          int nt2;
+          tile_coords<MODE>(tile + gridDim.x, m_tiles, n_tiles, a.reverse, mt2, nt2);
+          // one CTA per activation row block issues the prefetch (the block is shared by the n- / m-tiles)
+          const bool mine = a.shift_b ? (mt2 == 0) : (nt2 == 0);
+          if (mine) {
+            const long long span = a.shift_b ? BN : BM;
+            long long r0 = (a.shift_b ? (long long)nt2 * BN : mt2 * BM) - kHalo;
+            long long r1 = r0 + span + 2 * kHalo;
+            r0 = r0 < 0 ? 0 : r0;
+            r1 = r1 > a.act_rows ? a.act_rows : r1;
+            if (r1 > r0)
+              bulk_prefetch_l2(static_cast<const unsigned char*>(a.act_base) + r0 * a.act_ld_bytes,
+                               (unsigned)((r1 - r0) * a.act_ld_bytes));
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / a.kblocks_per_tap;
           const int d0 = (kb - tap * a.kblocks_per_tap) * BK;
@@ -359,25 +419,25 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ================= epilogue warps (2..9) =================
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;         // which 128 of the tile's 256 columns
+    const int colq = (warp - 2) >> 2;         // which kEpiCols of the tile's 256 columns
     const int et = threadIdx.x - 64;          // 0..255
     int staged_nt0 = -1, staged_nt1 = -1;     // n-tile whose epilogue vectors sit in s_vec[0] / s_vec[1]
     int it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       long long mt;
       int nt;
-      tile_coords<MODE>(tile, m_tiles, n_tiles, mt, nt);
+      tile_coords<MODE>(tile, m_tiles, n_tiles, a.reverse, mt, nt);
       const int col_base = nt * BN;
       const int acc = it & 1;
       const unsigned acc_phase = (unsigned)(it >> 1) & 1u;
       const long long row = mt * BM + quarter * 32 + lane;
       const unsigned taddr0 =
-          tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * BN) + (unsigned)(half * (BN / 2));
+          tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * BN) + (unsigned)(colq * kEpiCols);
 
       if (MODE == kModeStats) {
         // ---- per-unit running sums over the frames of the tile (stats_pooling.py:228-240) ----
         int* seg = s_seg + acc * BN;
-        {
+        if (et < BN) {
           const long long fr = (long long)col_base + et;
           seg[et] = (fr < a.n_rows) ? a.rowseg[fr] : -1;
         }
@@ -388,7 +448,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
 
-        const int* sg = seg + half * (BN / 2);
+        const int* sg = seg + colq * kEpiCols;
         float s = 0.0f, s2 = 0.0f;
         int cur = -1;
         auto flush = [&]() {
@@ -400,9 +460,9 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         unsigned r[2][32];
         tmem_ld32_issue(taddr0, r[0]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kEpiChunks; ++c) {
           tmem_ld_wait(r[c & 1]);
-          if (c + 1 < 4) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) & 1]);
+          if (c + 1 < kEpiChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) & 1]);
           const int* sc = sg + c * 32;
           const int first = sc[0], last = sc[31];
           if (first == last && first >= 0) {   // warp-uniform: the whole chunk lies inside one utterance
@@ -435,16 +495,19 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int have_nt = acc ? staged_nt1 : staged_nt0;
         if (have_nt != nt) {                                 // uniform over all epilogue threads
           asm volatile("bar.sync 1, 256;\n" ::: "memory");    // every warp is done reading the old vectors
-          const int col = col_base + et;
-          const bool ok = col < a.n_rows;
-          vb[et] = (ok && a.bias) ? a.bias[col] : 0.0f;
-          vb[BN + et] = (ok && a.scale) ? a.scale[col] : 1.0f;
-          vb[2 * BN + et] = (ok && a.offset) ? a.offset[col] : 0.0f;
+          if (et < BN) {
+            const int col = col_base + et;
+            const bool ok = col < a.n_rows;
+            vb[et] = (ok && a.bias) ? a.bias[col] : 0.0f;
+            vb[BN + et] = (ok && a.scale) ? a.scale[col] : 1.0f;
+            vb[2 * BN + et] = (ok && a.offset) ? a.offset[col] : 0.0f;
+          }
           asm volatile("bar.sync 1, 256;\n" ::: "memory");
           if (acc) staged_nt1 = nt; else staged_nt0 = nt;
         }
         int flags = 0;
         if (row < a.m_rows) flags = a.rowmap ? a.rowmap[row] : kRowStore;
+        if (a.debug & 1) flags = 0;
         float radd = 0.0f;
         if (MODE == kModeF32 && a.row_add != nullptr && row < a.m_rows) radd = a.row_add[row];
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -454,41 +517,25 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr bool kBf16 = (MODE == kModeBf16);
         constexpr int kEs = kBf16 ? 2 : 4;                   // output element size
         const long long ld_bytes = a.out_ld * kEs;
-        unsigned char* orow = reinterpret_cast<unsigned char*>(a.out) + row * ld_bytes;
         unsigned char* owarp = reinterpret_cast<unsigned char*>(a.out) + (mt * BM + quarter * 32) * ld_bytes;
         unsigned char* stg = s_stg + (warp - 2) * (32 * kStgPitch);
         const bool vec_ok = ((reinterpret_cast<unsigned long long>(a.out) | (unsigned long long)ld_bytes) & 15ull) == 0;
-        const bool do_store = (flags & kRowStore) != 0;
-        const int halo_lo = (flags & kRowFirst) ? kHalo : 0, halo_hi = (flags & kRowLast) ? kHalo : 0;
         const float relu_lo = a.relu ? 0.0f : -3.402823466e+38f;
-        unsigned r[2][32];
+        unsigned r[2][32];                                // TMEM loads run one chunk ahead of the math / stores
         tmem_ld32_issue(taddr0, r[0]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kEpiChunks; ++c) {
           tmem_ld_wait(r[c & 1]);
-          if (c + 1 < 4) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) & 1]);
-          const int cc = half * (BN / 2) + c * 32;        // column offset inside the tile
+          if (c + 1 < kEpiChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) & 1]);
+          const int cc = colq * kEpiCols + c * 32;        // column offset inside the tile
           const int col0 = col_base + cc;
-          if (col0 >= n_cols) continue;                   // warp-uniform
-          if (vec_ok && col0 + 32 <= n_cols) {
-            store_chunk<kBf16>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags,
-                               owarp + (long long)col0 * kEs, ld_bytes);
-          } else {
-            // ragged right edge (n_cols not a multiple of 32) or unaligned rows: element-wise stores
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = fmaxf(__uint_as_float(r[c & 1][i]) + vb[cc + i], relu_lo);
-              x = fmaf(x, vb[BN + cc + i], vb[2 * BN + cc + i]) + radd;
-              if (do_store && col0 + i < n_cols) {
-#pragma unroll 1
-                for (int h = -halo_lo; h <= halo_hi; ++h) {
-                  unsigned char* p = orow + h * ld_bytes + (long long)(col0 + i) * kEs;
-                  if (kBf16) *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(x);
-                  else *reinterpret_cast<float*>(p) = x;
-                }
-              }
-            }
-          }
+          if (col0 >= n_cols || (a.debug & 2)) continue;  // warp-uniform
+          unsigned char* out0 = owarp + (long long)col0 * kEs;
+          if (vec_ok && col0 + 32 <= n_cols)
+            store_chunk<kBf16, true>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, out0, ld_bytes, 32);
+          else
+            store_chunk<kBf16, false>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, out0, ld_bytes,
+                                      n_cols - col0);
         }
       }
       tc_fence_before();
@@ -727,6 +774,12 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& ar
   }
   const long long tiles = ((args.m_rows + BM - 1) / BM) * ((args.n_rows + BN - 1) / BN);
   if (tiles <= 0) return KTF_OK;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("KTF_TC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  const_cast<TcArgs&>(args).debug = dbg;
   const unsigned grid = (unsigned)std::min<long long>(tiles, ktf::num_sms());
   tdnn_tc_kernel<MODE><<<grid, kThreadsTc, kSmemTc, st>>>(tmA, tmB, args);
   KTF_LAUNCH_OK();
@@ -751,7 +804,7 @@ void fill_taps(TcArgs& args, const TcLayer& L, bool a_is_spliced, long long a_co
 // (implicit taps) or an already spliced matrix.
 int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, long long a_ld, long long a_cols,
               long long m_rows, const int* rowmap, void* out, long long out_ld, bool out_bf16, bool a_is_spliced,
-              cudaStream_t st) {
+              cudaStream_t st, int reverse = 0) {
   CUtensorMap tmA;
   int rc = encode_map(&tmA, A, (unsigned long long)a_cols, (unsigned long long)m_rows, (unsigned long long)a_ld, BK, BM);
   if (rc != KTF_OK) return rc;
@@ -759,6 +812,10 @@ int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, lon
   fill_taps(args, L, a_is_spliced, a_cols);
   args.m_rows = m_rows;
   args.n_rows = L.U;
+  args.act_base = A;
+  args.act_ld_bytes = a_ld * 2;
+  args.act_rows = m_rows;
+  args.reverse = reverse;
   args.rowmap = rowmap;
   args.bias = a->d_bias;
   args.scale = a->d_scale;
@@ -772,7 +829,8 @@ int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, lon
 // The layer that feeds StatsPooling: operands swapped (M = units, N = frames), epilogue accumulates
 // per-utterance sum / sum of squares of relu(acc + bias) into sums (batch, 2, U) (pre-zeroed).
 int run_layer_stats(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* X, long long x_ld, long long x_cols,
-                    long long frames, const int* rowseg, float* sums, bool x_is_spliced, cudaStream_t st) {
+                    long long frames, const int* rowseg, float* sums, bool x_is_spliced, cudaStream_t st,
+                    int reverse = 0) {
   CUtensorMap tmX;
   int rc = encode_map(&tmX, X, (unsigned long long)x_cols, (unsigned long long)frames, (unsigned long long)x_ld, BK, BN);
   if (rc != KTF_OK) return rc;
@@ -781,6 +839,10 @@ int run_layer_stats(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* 
   args.shift_b = 1;
   args.m_rows = L.U;
   args.n_rows = frames;
+  args.act_base = X;
+  args.act_ld_bytes = x_ld * 2;
+  args.act_rows = frames;
+  args.reverse = reverse;
   args.rowseg = rowseg;
   args.bias = a->d_bias;
   args.relu = a->cfg.activation == KTF_ACT_RELU;
@@ -1049,7 +1111,7 @@ int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int6
     if (i == s->stats_after) {
       // fused StatsPooling: the activation of this layer is never stored
       KTF_CUDA(cudaMemsetAsync(sums, 0, (size_t)batch * 2 * L.U * sizeof(float), st));
-      if ((rc = run_layer_stats(L, a, A, a_ld, a_cols, prow, rowseg, sums, spliced, st)) != KTF_OK) return rc;
+      if ((rc = run_layer_stats(L, a, A, a_ld, a_cols, prow, rowseg, sums, spliced, st, i & 1)) != KTF_OK) return rc;
       dim3 grid((unsigned)batch, (unsigned)((L.U + 127) / 128));
       stats_finalize_tc_kernel<<<grid, 128, 0, st>>>(sums, offs, L.U, a->d_scale, a->d_offset, s->include_std,
                                                      s->stats_eps, last ? nullptr : pooled, last ? out_dev : nullptr,
@@ -1069,7 +1131,9 @@ int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int6
     }
     __nv_bfloat16* y = buf[which];
     const long long y_ld = round_up(L.U, 8);
-    if ((rc = run_layer(L, a, A, a_ld, a_cols, prow, rowmap, y, y_ld, true, spliced, st)) != KTF_OK) return rc;
+    // serpentine: odd layers walk the row blocks backwards, starting on the rows the previous layer wrote
+    // last (still L2 resident) instead of the ones it wrote first (long evicted when activations > L2)
+    if ((rc = run_layer(L, a, A, a_ld, a_cols, prow, rowmap, y, y_ld, true, spliced, st, i & 1)) != KTF_OK) return rc;
     cur = y;
     cur_ld = y_ld;
     which ^= 1;
