@@ -12,6 +12,8 @@ Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed for rendez
 import torch
 import torch.distributed as dist
 
+from . import _tensor as T
+
 
 def world():
     if dist.is_available() and dist.is_initialized():
@@ -57,3 +59,55 @@ def plda_score_sharded(plda, x_test_local, x_enroll_local):
     u_enroll_local = plda.transformVector(x_enroll_local.contiguous())
     u_test = gather_rows(u_test_local)
     return plda.logLikelihoodRatio(u_test, u_enroll_local), u_test
+
+
+def stream_batches(fn, host_in, chunk, host_out=None):
+    """
+    Runs `fn` (any layer / model call taking a CUDA tensor of utterances and returning a CUDA tensor with
+    the same leading dimension) over a HOST batch in chunks of `chunk` utterances, with the host->device
+    copy of chunk i+1 and the device->host copy of result i-1 overlapped with the compute of chunk i
+    (two side streams; PCIe is full duplex).  Utterances are independent on this path, so the result equals
+    the one-shot call.  `host_in` should be pinned for the copies to be asynchronous; `host_out`, if given,
+    is a pinned tensor that receives the results, otherwise the device results are concatenated.
+    """
+    dev = T.device()
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = _side_streams(dev)
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    outs = []
+    n = host_in.shape[0]
+
+    def fetch(i):
+        with torch.cuda.stream(s_in):
+            x = host_in[i:i + chunk].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+        return x, ev
+
+    nxt = fetch(0) if n > 0 else None
+    for i in range(0, n, chunk):
+        x, ev = nxt
+        nxt = fetch(i + chunk) if i + chunk < n else None    # the next copy is in flight before this chunk computes
+        cur.wait_event(ev)
+        x.record_stream(cur)
+        y = fn(x)
+        if host_out is None:
+            outs.append(y)
+        else:
+            s_out.wait_stream(cur)
+            with torch.cuda.stream(s_out):
+                host_out[i:i + y.shape[0]].copy_(y, non_blocking=True)
+            y.record_stream(s_out)
+    cur.wait_stream(s_out)
+    return host_out if host_out is not None else torch.cat(outs, dim=0)
+
+
+_SIDE = {}
+
+
+def _side_streams(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _SIDE[key]

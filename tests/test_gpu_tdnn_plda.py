@@ -336,3 +336,40 @@ def test_xvector_extractor_from_config(ktf):
     ref = ktf.models.XvectorExtractor(extractor_cfg(), precision="f32", seed=0)(wav)
     # reference's own e2e tolerance with dither on (xvector_extractor_test.py:30)
     assert 1.0 - cosine(a, ref) <= 0.075
+
+
+def test_stream_batches_equals_one_shot(ktf):
+    # host batch processed in chunks with overlapped copies == the one-shot call (utterances are independent)
+    import torch
+    from kaldi_tflite_b200 import parallel
+    rng = np.random.default_rng(9)
+    host = torch.from_numpy((rng.standard_normal((10, 16000)) * 3000).astype(np.float32)).pin_memory()
+    fr = ktf.layers.Framing(dynamic_input_shape=True)
+    mf = ktf.layers.MFCC(num_mfccs=30, num_mels=30)
+    fn = lambda x: mf(fr(x))
+    want = fn(host.cuda())
+    got = parallel.stream_batches(fn, host, 3)
+    assert torch.equal(got, want)
+    out = torch.empty(tuple(want.shape), dtype=torch.float32).pin_memory()
+    parallel.stream_batches(fn, host, 4, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, want.cpu())
+
+
+def test_plda_tensor_core_path_large_vs_oracle(ktf):
+    # fp16 hi/lo split GEMM on the tcgen05 engine: ragged sizes (not multiples of the 128 x 256 tile),
+    # enroll != test, |delta| <= 1e-3 * max(|s|, 1) against the float64 oracle
+    import torch
+    dim, nt, ne = 128, 1037, 700
+    mean, Tm, psi = synthetic_plda(dim)
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((nt + ne, dim))
+    x = (x / np.linalg.norm(x, axis=1, keepdims=True) * np.sqrt(dim)).astype(np.float32)
+    layer = ktf.layers.PLDA(dim, mean, Tm, psi, dtype=np.float32, return_transformed=False)
+    u = layer.transformVector(torch.from_numpy(x).cuda())
+    got = layer.logLikelihoodRatio(u[:nt], u[nt:]).cpu().numpy()
+    uo = O.plda_transform(x, mean, Tm, psi, dtype=np.float64)
+    want = O.plda_llr(uo, psi)[:nt, nt:]
+    assert got.shape == want.shape == (nt, ne)
+    assert np.all(np.abs(got - want) <= 1e-3 * np.maximum(np.abs(want), 1.0))
+    assert np.max(np.abs(got - want)) < 2e-4          # fp32-equivalent: far inside the gate
