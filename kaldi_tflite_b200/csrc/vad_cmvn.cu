@@ -154,7 +154,7 @@ __global__ void vad_compact_kernel(const float* __restrict__ feats, int dim,
 
 // Sliding CMVN.  blockDim = (32 feature lanes, 8 sub-chunks); each y-slice owns kSub consecutive
 // output frames of one utterance and carries the window sum along them.
-constexpr int kCmvnSub = 32;
+constexpr int kCmvnSub = 128;   // frames per warp: the window sum is rebuilt once per sub-chunk, then slides
 constexpr int kCmvnY = 8;
 
 __global__ void cmvn_kernel(const float* __restrict__ in, int dim, const long long* __restrict__ offs,
@@ -199,14 +199,27 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int dim, const long lo
       }
     } else {                                                 // sliding window (cmvn.py:172-204)
       int ws = min(max(t0 - N / 2, 0), T - N);
-      float s = 0.0f, s2 = 0.0f;
-      for (int t = ws; t < ws + N; ++t) {
-        const float v = x[(long long)t * dim + d];
-        s += v;
-        s2 += __fmul_rn(v, v);
+      // window sum of the first frame of the sub-chunk: four independent partial sums (the loads are
+      // independent; a single accumulator would serialise N dependent adds)
+      float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+      int t = ws;
+      for (; t + 4 <= ws + N; t += 4) {
+        const float v0 = x[(long long)t * dim + d], v1 = x[(long long)(t + 1) * dim + d];
+        const float v2 = x[(long long)(t + 2) * dim + d], v3 = x[(long long)(t + 3) * dim + d];
+        p0 += v0; p1 += v1; p2 += v2; p3 += v3;
+        q0 += __fmul_rn(v0, v0); q1 += __fmul_rn(v1, v1); q2 += __fmul_rn(v2, v2); q3 += __fmul_rn(v3, v3);
       }
-      for (int t = t0; t < t1; ++t) {
-        const int want = min(max(t - N / 2, 0), T - N);
+      for (; t < ws + N; ++t) {
+        const float v = x[(long long)t * dim + d];
+        p0 += v;
+        q0 += __fmul_rn(v, v);
+      }
+      float s = (p0 + p1) + (p2 + p3), s2 = (q0 + q1) + (q2 + q3);
+      const float inv_n = 1.0f / (float)N;
+#pragma unroll 4
+      for (int tt = t0; tt < t1; ++tt) {
+        const int want = min(max(tt - N / 2, 0), T - N);
+        const float xc = x[(long long)tt * dim + d];
         if (want != ws) {  // advances by exactly one
           const float vo = x[(long long)ws * dim + d];
           const float vn = x[(long long)(ws + N) * dim + d];
@@ -214,10 +227,10 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int dim, const long lo
           s2 += __fmul_rn(vn, vn) - __fmul_rn(vo, vo);
           ws = want;
         }
-        const float mean = s / (float)N;
-        float v = x[(long long)t * dim + d] - mean;
-        if (norm_vars) v = v / sqrtf(s2 / (float)N - __fmul_rn(mean, mean));
-        out[(o0 + (t - ta)) * dim + d] = v;
+        const float mean = s * inv_n;
+        float v = xc - mean;
+        if (norm_vars) v = v / sqrtf(s2 * inv_n - __fmul_rn(mean, mean));
+        out[(o0 + (tt - ta)) * dim + d] = v;
       }
     }
   }
