@@ -87,14 +87,22 @@ class XvectorExtractor:
         fe = self.mfcc.frontend(self.framing.frameWidth, self.framing.frameShift)
         if self.mfcc.windowing.dither != 0.0:
             wav_flat = wav_flat + torch.randn_like(wav_flat) * float(self.mfcc.windowing.dither)
+        lens = np.diff(sample_offsets)
+        if len(lens) > 0 and bool(np.all(lens == lens[0])):
+            # uniform batch: no offset tables to upload, nothing on this path synchronises with the host
+            B, n = len(lens), int(lens[0])
+            feats, _ = fe.forward(wav_flat.reshape(B, n))
+            return feats.reshape(-1, feats.shape[-1]), T.uniform_offsets(B, feats.shape[1])
         feats, fo = fe.forward_ragged(wav_flat, sample_offsets)
         return feats, torch.from_numpy(fo).to(wav_flat.device)
 
     def embed(self, feats, offsets, max_frames=None):
         mask = self.vad.mask_ragged(feats, offsets)
         voiced, voffs, _ = self.vad.compact_ragged(feats, mask, offsets, gather=True)
-        if bool((voffs[1:] == voffs[:-1]).any().item()):
-            raise ValueError("an utterance has no voiced frames after VAD")
+        # An utterance without voiced frames has no statistics to pool (the reference's gather_nd / reduce_mean
+        # would produce NaN).  The flag stays on the device -- checking it here would stall the launch queue --
+        # and is examined when the result is handed back as a host array (see __call__).
+        self._no_voiced = (voffs[1:] == voffs[:-1]).any()
         normed, _ = self.cmvn.forward_ragged(voiced, voffs, max_frames=max_frames)
         emb, _ = self.xvec.forward_ragged(normed, voffs)
         return emb, mask, voffs
@@ -130,6 +138,8 @@ class XvectorExtractor:
         y = self.backend(emb)
         ref = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
         out = T.like_input(y.squeeze(), ref)                      # tf.squeeze (:184)
+        if not isinstance(out, torch.Tensor) and bool(self._no_voiced.item()):
+            raise ValueError("an utterance has no voiced frames after VAD")
         if return_intermediate:
             return out, {"mfcc": feats, "frame_offsets": offsets, "mask": mask,
                          "voiced_offsets": voffs, "embedding": emb}
