@@ -52,13 +52,21 @@ def _worker(rank, world, port, n_test, n_enroll, dim, out_dir):
             def transformVector(self, x):
                 return torch.from_numpy(O.plda_transform(x.numpy(), mean, Tm, psi, dtype=np.float64))
 
-            def logLikelihoodRatio(self, u_test, u_enroll):
+            def logLikelihoodRatio(self, u_test, u_enroll, out=None):
                 u = np.concatenate([u_test.numpy(), u_enroll.numpy()])
-                full = O.plda_llr(u, psi)
-                return torch.from_numpy(full[:u_test.shape[0], u_test.shape[0]:])
+                full = torch.from_numpy(O.plda_llr(u, psi)[:u_test.shape[0], u_test.shape[0]:])
+                if out is None:
+                    return full
+                out.copy_(full)
+                return out
 
         block, u_all = parallel.plda_score_sharded(Stub(), torch.from_numpy(x_test[tlo:thi]),
                                                    torch.from_numpy(x_enroll[elo:ehi]))
+        counts = [parallel.shard_range(n_test, r, world)[1] - parallel.shard_range(n_test, r, world)[0]
+                  for r in range(world)]
+        block2, _ = parallel.plda_score_sharded(Stub(), torch.from_numpy(x_test[tlo:thi]),
+                                                torch.from_numpy(x_enroll[elo:ehi]), test_counts=counts)
+        assert torch.equal(block, block2)
         np.save(os.path.join(out_dir, f"block{rank}.npy"), block.numpy())
         assert u_all.shape == (n_test, dim)
     finally:
