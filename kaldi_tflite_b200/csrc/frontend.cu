@@ -21,6 +21,7 @@
 //   * log, DCT (30x30-ish, from smem), lifter, C0 <- log-energy, coalesced store.
 // All synchronisation is __syncwarp; CTAs only share the constant tables.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -28,44 +29,11 @@
 #include "common.cuh"
 #include "twiddles64.h"
 
+#include "frontend_internal.cuh"
+
+using namespace ktf_fe;
+
 namespace {
-
-constexpr int kFramesPerWarp = 4;
-constexpr int kWarpsPerCta = 4;
-constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kMaxMels = 128;
-constexpr int kMaxCeps = 32;
-constexpr int kGroups = 8;  // the 8 lanes of a frame cooperate as 8 "groups" in the mel / DCT stages
-
-struct FrontendArgs {
-  // data
-  const float* wav;
-  float* out;
-  float* energy_out;
-  // uniform batch
-  long long wav_stride;
-  long long num_samples;
-  long long frames_per_utt;
-  long long groups_per_utt;
-  // ragged batch (all nullptr for uniform)
-  const long long* sample_offsets;
-  const long long* frame_offsets;
-  const long long* group_offsets;
-  long long batch;
-  long long total_groups;
-  // tables (global memory, copied to smem per CTA)
-  const float* window;     // [W]
-  const float2* stage_tw;  // [8][R+2]
-  const float2* post_tw;   // [C+1]  -i * W_{2C}^k
-  const int4* mel_filt;    // [M]  (first 4-bin chunk, #chunks, offset into mel_w, 0)
-  const float* mel_w;      // [mel_w_len] per-filter weights, chunk padded, prescaled
-  const float* dct;        // [M][32] packed as [i][g][r] -> coefficient g + 8r
-  const float* lifter;     // [32]
-  // config
-  int W, shift, span, M, Kc, out_dim, output, mel_w_len;
-  int remove_dc, raw_energy, use_energy, use_power, use_log, apply_lifter;
-  float preemph, energy_floor, eps;
-};
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -116,25 +84,6 @@ __device__ __forceinline__ void fft_dif(float2 (&x)[TOT]) {
   }
 }
 
-__device__ __forceinline__ float group_sum8(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
-  return v;
-}
-
-__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
 template <int R>
 struct Geo {
   static constexpr int C = 8 * R;          // complex FFT length
@@ -151,57 +100,6 @@ __device__ __forceinline__ int qidx(int k) {
   return ((c ^ ((c >> 3) & 7)) << 2) | (k & 3);
 }
 __device__ __forceinline__ int qchunk(int c) { return (c ^ ((c >> 3) & 7)) << 2; }
-
-struct Item {
-  long long utt_base, utt_len, out_row0, frame0;
-  int nvalid;
-};
-
-__device__ __forceinline__ Item decode_item(const FrontendArgs& a, long long item) {
-  Item it;
-  long long q, utt_frames;
-  if (a.group_offsets == nullptr) {
-    long long b;
-    if (a.total_groups < 0x7fffffffLL) b = (unsigned)item / (unsigned)a.groups_per_utt;   // 32-bit division
-    else b = item / a.groups_per_utt;
-    q = item - b * a.groups_per_utt;
-    it.utt_base = b * a.wav_stride;
-    it.utt_len = a.num_samples;
-    utt_frames = a.frames_per_utt;
-    it.out_row0 = b * a.frames_per_utt;
-  } else {
-    long long lo = 0, hi = a.batch;  // largest b with group_offsets[b] <= item
-    while (hi - lo > 1) {
-      const long long mid = (lo + hi) >> 1;
-      if (a.group_offsets[mid] <= item) lo = mid; else hi = mid;
-    }
-    q = item - a.group_offsets[lo];
-    it.utt_base = a.sample_offsets[lo];
-    it.utt_len = a.sample_offsets[lo + 1] - it.utt_base;
-    it.out_row0 = a.frame_offsets[lo];
-    utt_frames = a.frame_offsets[lo + 1] - it.out_row0;
-  }
-  it.frame0 = q * kFramesPerWarp;
-  it.nvalid = (int)min((long long)kFramesPerWarp, utt_frames - it.frame0);
-  return it;
-}
-
-// Asynchronously stages the item's sample span into the warp's smem buffer (zero filled past the
-// end of the utterance).  16-byte copies when source and length allow, 4-byte copies otherwise.
-__device__ __forceinline__ void stage_span(const FrontendArgs& a, const Item& it, float* s_span, int lane) {
-  const long long s0 = it.frame0 * a.shift;
-  const float* src = a.wav + it.utt_base + s0;
-  const long long avail = it.utt_len - s0;
-  if (avail >= a.span && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0)) {
-    const int n4 = a.span >> 2;
-    for (int i = lane; i < n4; i += 32) cp_async16(s_span + 4 * i, src + 4 * i);
-    for (int i = (n4 << 2) + lane; i < a.span; i += 32) cp_async4(s_span + i, src + i);
-  } else {
-    for (int i = lane; i < a.span; i += 32) {
-      if (i < avail) cp_async4(s_span + i, src + i); else s_span[i] = 0.0f;
-    }
-  }
-}
 
 // R = complex FFT length / 8.  MV > 0: frame width is exactly 16*MV and frame_shift is even, so the
 // windowing loop has compile-time bounds and 64-bit loads; MV == 0: any width <= 16R (runtime checks).
@@ -548,22 +446,6 @@ __global__ void framing_kernel(const float* __restrict__ wav, long long wav_stri
 
 }  // namespace
 
-struct ktf_frontend {
-  ktf_frontend_cfg cfg;
-  int R = 0;          // complex FFT length / 8
-  int C = 0;
-  int out_dim = 0;
-  int span = 0;
-  int mel_w_len = 4;
-  size_t smem_bytes = 0;
-  float* d_window = nullptr;
-  float2* d_stage_tw = nullptr;
-  float2* d_post_tw = nullptr;
-  int4* d_mel_filt = nullptr;
-  float* d_mel_w = nullptr;
-  float* d_dct = nullptr;
-  float* d_lifter = nullptr;
-};
 
 namespace {
 
@@ -602,6 +484,7 @@ int launch(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
 }
 
 int dispatch(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
+  if (fe->d_r16 != nullptr) return r16_launch(fe, a, st);
   const int W = fe->cfg.frame_width;
   const bool even_shift = (fe->cfg.frame_shift & 1) == 0;
   if (fe->R == 32) {
@@ -640,6 +523,10 @@ void fill_args(const ktf_frontend* fe, FrontendArgs& a) {
   a.preemph = c.preemphasis;
   a.energy_floor = c.energy_floor;
   a.eps = c.epsilon;
+  a.r16_blob = fe->d_r16;
+  a.r16_blob_floats = fe->r16_blob_floats;
+  a.r16_nf = fe->r16_nf;
+  a.r16_melw_floats = fe->r16_melw_floats;
 }
 
 }  // namespace
@@ -732,6 +619,8 @@ int ktf_frontend_create(const ktf_frontend_cfg* cfg, const float* window_host,
     if ((rc = ktf::upload(&fe->d_dct, dp.data(), dp.size())) != KTF_OK) return fail(rc);
     if ((rc = ktf::upload(&fe->d_lifter, lf.data(), lf.size())) != KTF_OK) return fail(rc);
   }
+  if (getenv("KTF_FRONTEND_GENERIC") == nullptr &&
+      (rc = r16_build(fe, window_host, mel_bank_host, dct_host, lifter_host)) != KTF_OK) return fail(rc);
   fe->smem_bytes = (R == 32) ? smem_for<32>(fe) : smem_for<16>(fe);
   if (fe->smem_bytes > 227 * 1024) {
     ktf::set_error("front-end configuration needs %zu bytes of shared memory (> 227 KB)", fe->smem_bytes);
@@ -750,6 +639,7 @@ void ktf_frontend_destroy(ktf_frontend* fe) {
   cudaFree(fe->d_mel_w);
   cudaFree(fe->d_dct);
   cudaFree(fe->d_lifter);
+  cudaFree(fe->d_r16);
   delete fe;
 }
 

@@ -1,0 +1,146 @@
+// Internals shared by the front-end translation units (frontend.cu: generic radix-2 kernel and the
+// C-ABI; frontend_r16.cu: the 16 x 16 fast path for 512-point FFTs).
+#pragma once
+
+#include "common.cuh"
+
+namespace ktf_fe {
+
+constexpr int kFramesPerWarp = 4;
+constexpr int kWarpsPerCta = 4;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kMaxMels = 128;
+constexpr int kMaxCeps = 32;
+constexpr int kGroups = 8;  // the 8 lanes of a frame cooperate as 8 "groups" in the mel / DCT stages
+
+struct FrontendArgs {
+  // data
+  const float* wav;
+  float* out;
+  float* energy_out;
+  // uniform batch
+  long long wav_stride;
+  long long num_samples;
+  long long frames_per_utt;
+  long long groups_per_utt;
+  // ragged batch (all nullptr for uniform)
+  const long long* sample_offsets;
+  const long long* frame_offsets;
+  const long long* group_offsets;
+  long long batch;
+  long long total_groups;
+  // tables (global memory, copied to smem per CTA)
+  const float* window;     // [W]
+  const float2* stage_tw;  // [8][R+2]
+  const float2* post_tw;   // [C+1]  -i * W_{2C}^k
+  const int4* mel_filt;    // [M]  (first 4-bin chunk, #chunks, offset into mel_w, 0)
+  const float* mel_w;      // [mel_w_len] per-filter weights, chunk padded, prescaled
+  const float* dct;        // [M][32] packed as [i][g][r] -> coefficient g + 8r
+  const float* lifter;     // [32]
+  // config
+  int W, shift, span, M, Kc, out_dim, output, mel_w_len;
+  int remove_dc, raw_energy, use_energy, use_power, use_log, apply_lifter;
+  float preemph, energy_floor, eps;
+  // 16 x 16 fast path (frontend_r16.cu): one blob laid out like the CTA's table region
+  const float* r16_blob;
+  int r16_blob_floats, r16_nf, r16_melw_floats;
+};
+
+__device__ __forceinline__ float group_sum8(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+__device__ __forceinline__ void cp_async4(unsigned dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+struct Item {
+  long long utt_base, utt_len, out_row0, frame0;
+  int nvalid;
+};
+
+__device__ __forceinline__ Item decode_item(const FrontendArgs& a, long long item) {
+  Item it;
+  long long q, utt_frames;
+  if (a.group_offsets == nullptr) {
+    long long b;
+    if (a.total_groups < 0x7fffffffLL) b = (unsigned)item / (unsigned)a.groups_per_utt;   // 32-bit division
+    else b = item / a.groups_per_utt;
+    q = item - b * a.groups_per_utt;
+    it.utt_base = b * a.wav_stride;
+    it.utt_len = a.num_samples;
+    utt_frames = a.frames_per_utt;
+    it.out_row0 = b * a.frames_per_utt;
+  } else {
+    long long lo = 0, hi = a.batch;  // largest b with group_offsets[b] <= item
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) >> 1;
+      if (a.group_offsets[mid] <= item) lo = mid; else hi = mid;
+    }
+    q = item - a.group_offsets[lo];
+    it.utt_base = a.sample_offsets[lo];
+    it.utt_len = a.sample_offsets[lo + 1] - it.utt_base;
+    it.out_row0 = a.frame_offsets[lo];
+    utt_frames = a.frame_offsets[lo + 1] - it.out_row0;
+  }
+  it.frame0 = q * kFramesPerWarp;
+  it.nvalid = (int)min((long long)kFramesPerWarp, utt_frames - it.frame0);
+  return it;
+}
+
+// Asynchronously stages the item's sample span into the warp's smem buffer (zero filled past the
+// end of the utterance).  16-byte copies when source and length allow, 4-byte copies otherwise.
+__device__ __forceinline__ void stage_span(const FrontendArgs& a, const Item& it, float* s_span, int lane) {
+  const long long s0 = it.frame0 * a.shift;
+  const float* src = a.wav + it.utt_base + s0;
+  const long long avail = it.utt_len - s0;
+  const unsigned sdst = (unsigned)__cvta_generic_to_shared(s_span);
+  if (avail >= a.span && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0)) {
+    const int n4 = a.span >> 2;
+    for (int i = lane; i < n4; i += 32) cp_async16(sdst + 16u * i, src + 4 * i);
+    for (int i = (n4 << 2) + lane; i < a.span; i += 32) cp_async4(sdst + 4u * i, src + i);
+  } else {
+    for (int i = lane; i < a.span; i += 32) {
+      if (i < avail) cp_async4(sdst + 4u * i, src + i); else s_span[i] = 0.0f;
+    }
+  }
+}
+
+}  // namespace ktf_fe
+
+struct ktf_frontend {
+  ktf_frontend_cfg cfg;
+  int R = 0;          // complex FFT length / 8
+  int C = 0;
+  int out_dim = 0;
+  int span = 0;
+  int mel_w_len = 4;
+  size_t smem_bytes = 0;
+  float* d_window = nullptr;
+  float2* d_stage_tw = nullptr;
+  float2* d_post_tw = nullptr;
+  int4* d_mel_filt = nullptr;
+  float* d_mel_w = nullptr;
+  float* d_dct = nullptr;
+  float* d_lifter = nullptr;
+  // 16 x 16 fast path (frontend_r16.cu); null when the configuration is not eligible
+  float* d_r16 = nullptr;
+  int r16_blob_floats = 0, r16_nf = 0, r16_melw_floats = 0;
+};
+
+namespace ktf_fe {
+// Builds the fast-path tables when the configuration is eligible (512-point FFT, 400-sample frames, power
+// spectrum, log mel, DC removal); leaves fe->d_r16 == nullptr otherwise.  Returns KTF_OK or an error.
+int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_host, const float* dct_host,
+              const float* lifter_host);
+int r16_launch(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st);
+}  // namespace ktf_fe

@@ -1,0 +1,616 @@
+// Fast path of the fused front-end for the common Kaldi geometry: 400-sample frames, 512-point FFT
+// (25 ms @ 16 kHz), power spectrum, MFCC or log-mel output.  Same math and the same reference lines
+// as frontend.cu (framing.py:243-265, windowing.py:180-209, filterbank.py:225-242, dct.py:175-176,
+// mfcc.py:197-244); what changes is the instruction budget per frame:
+//
+//   * the real FFT of length 512 is a 256-point complex FFT factored 16 x 16.  A frame is owned by 8
+//     lanes (4 frames per warp); in both stages a lane runs TWO 16-point FFTs held entirely in
+//     registers (radix-4 x radix-4, compile-time twiddles):
+//       stage 1  lane j owns n2 = 2j, 2j+1 : one LDS.128 per 32-sample row feeds both FFTs
+//       twiddle  W_256^(n2 k1) from a per-lane table, written as [k1][n2] rows with STS.128
+//       stage 2  lane j owns the columns k1 = j and 16-j (lane 0: 0 and 8), read back with LDS.128.
+//     Columns j and 16-j hold exactly the bin pairs (k, 256-k) the real-FFT untangling needs, so the
+//     power spectrum is produced without any further exchange.  Lane 0's two self-paired columns use
+//     the same instruction stream with a handful of selects (no divergent path), the Nyquist bin is
+//     never computed (its mel weight is identically zero, filterbank.py:176-187).
+//   * every shared-memory address is "per-lane base + immediate"; runtime configuration that the old
+//     kernel tested per frame is a template parameter or folded into the tables (lifter into the DCT
+//     matrix, the 1/4 of the untangling into the mel weights).
+//   * the mel filters are distributed over the 8 lanes of a frame by a host-side longest-first
+//     schedule, so the lanes' chunk counts are balanced.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "frontend_internal.cuh"
+
+using namespace ktf_fe;
+
+namespace {
+
+constexpr int kW = 400;               // frame width of the fast path
+constexpr int kRows = 13;             // ceil(400 / 32) rows of 32 samples
+constexpr int kTailLanes = 4;         // lanes j < 4 own valid samples in row 12 (400 = 12 * 32 + 16)
+constexpr int kWinPad = 416;          // window table padded with zeros to 13 * 32
+constexpr int kRowStride = 36;        // floats per [k1] row of the exchange tile (32 + 4: LDS.128 conflict-free)
+constexpr int kTile = 584;            // floats per frame tile (16 * 36 = 576, +8 so that frames shift by 8 banks)
+constexpr int kOffWin = 0;
+// per-lane table rows are padded to a stride of 4 (mod 32) floats: the 8 lanes of a frame (one LDS.128
+// quarter-warp) then read 8 different bank groups
+constexpr int kTw1Stride = 68;                  // floats per lane: [16 k1][4] + 4
+constexpr int kTw2Stride = 36;                  // floats per lane: [16 e][2] + 4
+constexpr int kOffTw1 = kOffWin + kWinPad;
+constexpr int kOffTw2 = kOffTw1 + 8 * kTw1Stride;
+constexpr int kOffUnits = kOffTw2 + 8 * kTw2Stride;  // [8 lanes][SD] unit descriptors, then [8 lanes][SW] unit weights
+__host__ __device__ constexpr int pad4mod32(int x) { return x + (((4 - x) % 32) + 32) % 32; }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// x * W_16^M with compile-time M (W_16 = exp(-2 pi i / 16)).
+template <int M>
+__device__ __forceinline__ float2 mul_w16(float2 x) {
+  constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+  if constexpr (M == 0) return x;
+  else if constexpr (M == 1) return make_float2(fmaf(x.x, c1, x.y * s1), fmaf(x.y, c1, -x.x * s1));
+  else if constexpr (M == 2) return make_float2((x.x + x.y) * h, (x.y - x.x) * h);
+  else if constexpr (M == 3) return make_float2(fmaf(x.x, s1, x.y * c1), fmaf(x.y, s1, -x.x * c1));
+  else if constexpr (M == 4) return make_float2(x.y, -x.x);
+  else if constexpr (M == 6) return make_float2((x.y - x.x) * h, -(x.x + x.y) * h);
+  else if constexpr (M == 9) return make_float2(fmaf(-x.x, c1, -x.y * s1), fmaf(-x.y, c1, x.x * s1));
+  else return x;
+}
+
+// 4-point DFT of (a, b, c, d) in place: a <- y0, b <- y1, c <- y2, d <- y3.
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
+  const float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = csub(b, d);
+  a = cadd(s0, s2);
+  c = csub(s0, s2);
+  b = make_float2(s1.x + s3.y, s1.y - s3.x);
+  d = make_float2(s1.x - s3.y, s1.y + s3.x);
+}
+
+// 16-point complex FFT in registers (radix 4 x 4, decimation in frequency).  Input natural order,
+// output X[k] at x[pos16(k)].
+__host__ __device__ constexpr int pos16(int k) { return 4 * (k & 3) + (k >> 2); }
+
+__device__ __forceinline__ void fft16(float2 (&x)[16]) {
+  // layer A: butterflies over (i, i+4, i+8, i+12); output q of butterfly i, times W_16^(i q), lands at 4q + i
+  dft4(x[0], x[4], x[8], x[12]);
+  dft4(x[1], x[5], x[9], x[13]);
+  dft4(x[2], x[6], x[10], x[14]);
+  dft4(x[3], x[7], x[11], x[15]);
+  x[5] = mul_w16<1>(x[5]);   x[9] = mul_w16<2>(x[9]);   x[13] = mul_w16<3>(x[13]);
+  x[6] = mul_w16<2>(x[6]);   x[10] = mul_w16<4>(x[10]); x[14] = mul_w16<6>(x[14]);
+  x[7] = mul_w16<3>(x[7]);   x[11] = mul_w16<6>(x[11]); x[15] = mul_w16<9>(x[15]);
+  // layer B: 4-point DFT over i inside each group q; output r of group q is X[4r + q] at 4q + r
+  dft4(x[0], x[1], x[2], x[3]);
+  dft4(x[4], x[5], x[6], x[7]);
+  dft4(x[8], x[9], x[10], x[11]);
+  dft4(x[12], x[13], x[14], x[15]);
+}
+
+// DCT_REG (MFCC with <= 32 mel bins): lane c keeps column c of the DCT matrix in registers and produces cepstrum
+// c of all 4 frames, so the DCT reads no table at all (only broadcast loads of the log-mel rows).
+template <int OUTPUT, bool RAW_ENERGY, bool DCT_REG>
+__global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const FrontendArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int NU = a.r16_nf;                        // mel units (8 bins each) per lane
+  const int SD = pad4mod32(2 * (NU + 1)), SW = pad4mod32(8 * NU);
+  const int M = a.M;
+  float* s_win = smem + kOffWin;
+  const float4* s_tw1 = reinterpret_cast<const float4*>(smem + kOffTw1);
+  const float4* s_tw2 = reinterpret_cast<const float4*>(smem + kOffTw2);
+  const float* s_udesc = smem + kOffUnits;
+  const float* s_uwts = s_udesc + 8 * SD;
+  const float* s_dct = s_uwts + 8 * SW;
+  float* s_warp0 = smem + a.r16_blob_floats;
+
+  const int span_p = ((a.span + 3) & ~3) + 16;     // row 12 of the last frame reads 16 floats past the span
+  const int LMS = ((M + 3) & ~3) + 4;               // log-mel row stride (one spare slot for padding filters)
+  const int out_row = (OUTPUT == KTF_OUT_MFCC) ? a.Kc : M;
+  const int out_sz = (4 * out_row + 3) & ~3;
+  const int warp_floats = span_p + 4 * kTile + 4 * LMS + out_sz;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_span = s_warp0 + warp * warp_floats;
+  float* s_T = s_span + span_p;
+  float* s_LM = s_T + 4 * kTile;             // mel sums, then log-mel [f][LMS]
+  float* s_out = s_LM + 4 * LMS;
+
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerCta + warp;
+  const long long warp_stride = (long long)gridDim.x * kWarpsPerCta;
+
+  Item cur;
+  long long item = warp_global;
+  if (item < a.total_groups) {
+    cur = decode_item(a, item);
+    stage_span(a, cur, s_span, lane);
+  }
+  for (int i = threadIdx.x; i < a.r16_blob_floats; i += kThreads) smem[i] = a.r16_blob[i];
+  for (int i = lane; i < 4 * LMS; i += 32) s_LM[i] = 0.0f;   // slots >= M stay finite
+  __syncthreads();
+
+  const int f = lane >> 3;
+  const int j = lane & 7;
+  const bool j0 = (j == 0);
+  const bool tail_ok = j < kTailLanes;
+
+  // per-lane bases: everything below is base + immediate
+  const float* fr = s_span + f * a.shift + 4 * j;
+  const float* wn = s_win + 4 * j;
+  const float4* tw1 = s_tw1 + j * (kTw1Stride / 4);
+  const float4* tw2 = s_tw2 + j * (kTw2Stride / 4);
+  float* tile = s_T + f * kTile;
+  float* tile_w = tile + 4 * j;
+  const int col_a = j, col_b = j0 ? 8 : 16 - j;
+  const float* row_a = tile + col_a * kRowStride;
+  const float* row_b = tile + col_b * kRowStride;
+  // power-spectrum bins written by evaluation e: A + 16 e and B + 16 (15 - e)
+  float* qa_lo = tile + j;                       // e < 8
+  float* qa_hi = tile + (j0 ? 8 : j);            // e >= 8
+  float* qb_lo = tile + 16 - j;                  // e < 8  (lane 0: 256 - 16 e)
+  float* qb_hi = tile + (j0 ? 8 : 16 - j);       // e >= 8
+  const int2* udesc = reinterpret_cast<const int2*>(s_udesc + j * SD);
+  const float4* uwts = reinterpret_cast<const float4*>(s_uwts + j * SW);
+  float* lm_acc = s_LM + f * LMS;
+  float* lm_row = (OUTPUT == KTF_OUT_MFCC) ? s_LM + f * LMS : s_out + f * M;
+  const float pc = a.preemph > 0.0f ? a.preemph : 0.0f;
+  const int prev_lane = (lane & 24) | ((j + 7) & 7);   // the lane that owns the 4 samples before mine
+  float dreg[DCT_REG ? 32 : 1];
+  if (DCT_REG) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dreg[i] = (i < M && lane < a.Kc) ? s_dct[i * 32 + lane] : 0.0f;
+  }
+
+  for (; item < a.total_groups; item += warp_stride) {
+    cp_async_wait_all();
+    __syncwarp();
+
+    // ---- windowing (windowing.py:180-209): rows of 32 samples, lane j owns samples 4j .. 4j+3 of a row
+    float2 ze[16], zo[16];
+    float esum = 0.0f;
+    {
+      float4 xv[kRows];
+      float xm[kRows];
+      float sum = 0.0f;
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        xv[r] = *reinterpret_cast<const float4*>(fr + 32 * r);
+        if (r == kRows - 1 && !tail_ok) xv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // sample 32r + 4j - 1 is the last of the previous lane's four (lane 0: lane 7's four of the previous row)
+        const float give = (r > 0 && j == 7) ? xv[r - 1].w : xv[r].w;
+        xm[r] = __shfl_sync(0xffffffffu, give, prev_lane);
+        sum += (xv[r].x + xv[r].y) + (xv[r].z + xv[r].w);
+      }
+      float mean = 0.0f;
+      if (a.remove_dc) mean = group_sum8(sum) / (float)kW;
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const float4 w = *reinterpret_cast<const float4*>(wn + 32 * r);
+        float d0 = xv[r].x - mean, d1 = xv[r].y - mean, d2 = xv[r].z - mean, d3 = xv[r].w - mean;
+        float dm = xm[r] - mean;
+        if (r == 0) dm = j0 ? d0 : dm;
+        if (r == kRows - 1 && !tail_ok) { d0 = 0.f; d1 = 0.f; d2 = 0.f; d3 = 0.f; dm = 0.f; }
+        if (RAW_ENERGY) esum = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, esum))));
+        const float y0 = (d0 - pc * dm) * w.x;
+        const float y1 = (d1 - pc * d0) * w.y;
+        const float y2 = (d2 - pc * d1) * w.z;
+        const float y3 = (d3 - pc * d2) * w.w;
+        if (!RAW_ENERGY) esum = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, esum))));
+        ze[r] = make_float2(y0, y1);
+        zo[r] = make_float2(y2, y3);
+      }
+#pragma unroll
+      for (int r = kRows; r < 16; ++r) { ze[r] = make_float2(0.f, 0.f); zo[r] = make_float2(0.f, 0.f); }
+    }
+    __syncwarp();  // every lane is done with the span buffer
+
+    // ---- prefetch the next item's span into the same buffer ----------------------------
+    const Item me = cur;
+    {
+      const long long nxt = item + warp_stride;
+      if (nxt < a.total_groups) {
+        cur = decode_item(a, nxt);
+        stage_span(a, cur, s_span, lane);
+      }
+    }
+
+    float log_e = 0.0f;
+    if (a.use_energy) {
+      esum = group_sum8(esum);
+      log_e = logf(fmaxf(esum, 0.0f) + a.eps);
+      log_e = fminf(fmaxf(log_e, a.energy_floor), 3.402823466e+38f);
+    }
+
+    // ---- stage 1: two 16-point FFTs over n1, twiddle W_256^(n2 k1), rows [k1][n2] of the tile ---------
+    float4 t1[16];   // issued ahead of the FFTs so that their latency is covered by arithmetic
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1) t1[k1] = tw1[k1];
+    fft16(ze);
+#pragma unroll
+    for (int k1 = 8; k1 < 16; ++k1) t1[k1] = tw1[k1];
+    fft16(zo);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+      float2 e = ze[pos16(k1)], o = zo[pos16(k1)];
+      if (k1 > 0) {
+        const float4 t = t1[k1];
+        e = cmul(e, make_float2(t.x, t.y));
+        o = cmul(o, make_float2(t.z, t.w));
+      }
+      *reinterpret_cast<float4*>(tile_w + k1 * kRowStride) = make_float4(e.x, e.y, o.x, o.y);
+    }
+    __syncwarp();
+
+    // ---- stage 2: columns a and b over n2 ---------------------------------------------------------------
+    float2 va[16], vb[16];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 ra = *reinterpret_cast<const float4*>(row_a + 4 * c);
+      const float4 rb = *reinterpret_cast<const float4*>(row_b + 4 * c);
+      va[2 * c] = make_float2(ra.x, ra.y);
+      va[2 * c + 1] = make_float2(ra.z, ra.w);
+      vb[2 * c] = make_float2(rb.x, rb.y);
+      vb[2 * c + 1] = make_float2(rb.z, rb.w);
+    }
+    float4 t2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t2[e] = tw2[e];
+    __syncwarp();  // the tile is consumed; it is reused as the power buffer below
+    fft16(va);
+    fft16(vb);
+
+    // ---- real-FFT untangling + |X|^2 (x4; the 1/4 sits in the mel weights) ----------------------------------
+    // evaluation e pairs zk = Z[k] with zp = Z[256 - k]:  4|X[k]|^2 = |S + G|^2, 4|X[256-k]|^2 = |S - G|^2,
+    // S = zk + conj(zp), G = (-i W_512^k) (zk - conj(zp)).
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float2 zk, zp;
+      if (e < 8) {
+        zk = va[pos16(e)];
+        const float2 p_self = va[pos16((16 - e) & 15)], p_reg = vb[pos16(15 - e)];
+        zp = make_float2(j0 ? p_self.x : p_reg.x, j0 ? p_self.y : p_reg.y);
+      } else {
+        const float2 k_self = vb[pos16(e)], k_reg = va[pos16(e)];
+        zk = make_float2(j0 ? k_self.x : k_reg.x, j0 ? k_self.y : k_reg.y);
+        zp = vb[pos16(15 - e)];
+      }
+      const float4 t4 = t2[e >> 1];
+      const float2 t = (e & 1) ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
+      const float2 S = make_float2(zk.x + zp.x, zk.y - zp.y);
+      const float2 D = make_float2(zk.x - zp.x, zk.y + zp.y);
+      const float2 G = cmul(t, D);
+      const float2 u = cadd(S, G), v = csub(S, G);
+      const float p1 = fmaf(u.x, u.x, u.y * u.y);
+      float p2 = fmaf(v.x, v.x, v.y * v.y);
+      float* dst1 = (e < 8 ? qa_lo : qa_hi) + 16 * e;
+      float* dst2 = (e < 8 ? qb_lo : qb_hi) + 16 * (15 - e);
+      if (e == 0) {   // lane 0: the partner of bin 0 is the Nyquist bin (unused); store bin 128 = conj(Z[128]) instead
+        const float2 z8 = va[pos16(8)];
+        const float p128 = 4.0f * fmaf(z8.x, z8.x, z8.y * z8.y);
+        p2 = j0 ? p128 : p2;
+        dst2 = j0 ? tile + 128 : dst2;
+      }
+      *dst1 = p1;
+      *dst2 = p2;
+    }
+    __syncwarp();
+
+    // ---- mel bank (filterbank.py:238-240): lane j walks its NU units of 8 bins; the units of a filter are
+    //      consecutive on one lane, the running sum is flushed at the filter's last unit.
+    float run = 0.0f, keep = 0.0f;
+    int2 d = udesc[0];   // (first bin | filter slot << 16, keep)
+#pragma unroll 2
+    for (int u = 0; u < NU; ++u) {
+      const float* q = tile + (d.x & 0xffff);
+      const float4 q0 = *reinterpret_cast<const float4*>(q);
+      const float4 q1 = *reinterpret_cast<const float4*>(q + 4);
+      const float4 w0 = uwts[2 * u];
+      const float4 w1 = uwts[2 * u + 1];
+      const int slot = d.x >> 16;
+      const float keep_next = __int_as_float(d.y);
+      d = udesc[u + 1];   // one padding descriptor follows the last unit
+      float acc0 = w0.x * q0.x, acc1 = w1.x * q1.x;
+      acc0 = fmaf(w0.y, q0.y, acc0);
+      acc1 = fmaf(w1.y, q1.y, acc1);
+      acc0 = fmaf(w0.z, q0.z, acc0);
+      acc1 = fmaf(w1.z, q1.z, acc1);
+      acc0 = fmaf(w0.w, q0.w, acc0);
+      acc1 = fmaf(w1.w, q1.w, acc1);
+      // the only serial dependency between units: keep = 1 inside a filter, 0 after its last unit
+      run = fmaf(run, keep, acc0 + acc1);
+      keep = keep_next;
+      lm_acc[slot] = run;   // partial sums are overwritten by the filter's last unit (same lane, program order)
+    }
+    __syncwarp();
+    // log (filterbank.py:240); each lane finishes mel bins 4j .. 4j+3 (+32, +64, ...) of its frame
+    for (int i0 = 4 * j; i0 < M; i0 += 32) {
+      float4 v = *reinterpret_cast<const float4*>(lm_acc + i0);
+      // __logf (MUFU.LG2 * ln2): absolute error <= ~2e-6 on log-mel values of magnitude ~20, two orders below the
+      // float32 noise of the spectrum itself; the frame log-energy (VAD input) keeps the exact logf
+      if (a.use_log) {
+        v.x = __logf(fmaxf(v.x, 0.0f) + a.eps);
+        v.y = __logf(fmaxf(v.y, 0.0f) + a.eps);
+        v.z = __logf(fmaxf(v.z, 0.0f) + a.eps);
+        v.w = __logf(fmaxf(v.w, 0.0f) + a.eps);
+      }
+      if (OUTPUT == KTF_OUT_MFCC) {
+        *reinterpret_cast<float4*>(lm_acc + i0) = v;
+      } else {
+        if (i0 < M) lm_row[i0] = v.x;
+        if (i0 + 1 < M) lm_row[i0 + 1] = v.y;
+        if (i0 + 2 < M) lm_row[i0 + 2] = v.z;
+        if (i0 + 3 < M) lm_row[i0 + 3] = v.w;
+      }
+    }
+    __syncwarp();
+
+    if (OUTPUT == KTF_OUT_MFCC && DCT_REG) {
+      // ---- DCT (dct.py:176) with the lifter (mfcc.py:212) folded into the matrix: lane c = cepstrum c of all 4 frames
+      float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int i4 = 0; i4 < 8; ++i4) {
+        if (4 * i4 < M) {
+#pragma unroll
+          for (int ff = 0; ff < 4; ++ff) {
+            const float4 lm = *reinterpret_cast<const float4*>(s_LM + ff * LMS + 4 * i4);   // broadcast
+            o[ff] = fmaf(lm.x, dreg[4 * i4], o[ff]);
+            o[ff] = fmaf(lm.y, dreg[4 * i4 + 1], o[ff]);
+            o[ff] = fmaf(lm.z, dreg[4 * i4 + 2], o[ff]);
+            o[ff] = fmaf(lm.w, dreg[4 * i4 + 3], o[ff]);
+          }
+        }
+      }
+      // C0 <- log-energy (mfcc.py:219-228): frame ff's value lives in lanes 8 ff .. 8 ff + 7
+#pragma unroll
+      for (int ff = 0; ff < 4; ++ff) {
+        const float le = __shfl_sync(0xffffffffu, log_e, 8 * ff);
+        if (lane == 0 && a.use_energy) o[ff] = le;
+      }
+      if (lane < a.Kc) {
+        float* dst = a.out + (me.out_row0 + me.frame0) * (long long)a.Kc + lane;
+#pragma unroll
+        for (int ff = 0; ff < 4; ++ff)
+          if (ff < me.nvalid) dst[ff * a.Kc] = o[ff];
+      }
+      continue;
+    }
+
+    if (OUTPUT == KTF_OUT_MFCC) {
+      // ---- DCT from the shared-memory table (more than 32 mel bins): lane (f, j) = cepstra 4j .. 4j+3 of frame f
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const float* dcol = s_dct + 4 * j;
+      const int M4 = M & ~3;
+      for (int i = 0; i < M4; i += 4) {
+        const float4 lm = *reinterpret_cast<const float4*>(lm_row + i);
+        const float lmv[4] = {lm.x, lm.y, lm.z, lm.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 d = *reinterpret_cast<const float4*>(dcol + (i + u) * 32);
+          acc[0] = fmaf(lmv[u], d.x, acc[0]);
+          acc[1] = fmaf(lmv[u], d.y, acc[1]);
+          acc[2] = fmaf(lmv[u], d.z, acc[2]);
+          acc[3] = fmaf(lmv[u], d.w, acc[3]);
+        }
+      }
+      for (int i = M4; i < M; ++i) {
+        const float lm = lm_row[i];
+        const float4 d = *reinterpret_cast<const float4*>(dcol + i * 32);
+        acc[0] = fmaf(lm, d.x, acc[0]);
+        acc[1] = fmaf(lm, d.y, acc[1]);
+        acc[2] = fmaf(lm, d.z, acc[2]);
+        acc[3] = fmaf(lm, d.w, acc[3]);
+      }
+      if (j0 && a.use_energy) acc[0] = log_e;
+      float* orow = s_out + f * a.Kc + 4 * j;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (4 * j + r < a.Kc) orow[r] = acc[r];
+      __syncwarp();
+    }
+
+    // ---- coalesced store of the group's nvalid x out_row tile ----------------------------------------------
+    {
+      float* dst = a.out + (me.out_row0 + me.frame0) * (long long)out_row;
+      const int n = me.nvalid * out_row;
+      if (((n & 3) == 0) && ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0)) {
+        const int n4 = n >> 2;
+        for (int i = lane; i < n4; i += 32)
+          reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_out)[i];
+      } else {
+        for (int i = lane; i < n; i += 32) dst[i] = s_out[i];
+      }
+    }
+  }
+}
+
+size_t r16_smem_bytes(const ktf_frontend* fe) {
+  const int M = fe->cfg.num_mels;
+  const int span_p = ((fe->span + 3) & ~3) + 16;
+  const int LMS = ((M + 3) & ~3) + 4;
+  const int out_row = fe->out_dim;
+  const int out_sz = (4 * out_row + 3) & ~3;
+  const size_t warp_floats = (size_t)span_p + 4 * kTile + 4 * LMS + out_sz;
+  return ((size_t)fe->r16_blob_floats + kWarpsPerCta * warp_floats) * sizeof(float);
+}
+
+template <int OUTPUT, bool RAW, bool DCT_REG>
+int launch_r16(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
+  const size_t smem = r16_smem_bytes(fe);
+  auto kern = frontend_r16_kernel<OUTPUT, RAW, DCT_REG>;
+  KTF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)std::max<size_t>(smem, 48 * 1024)));
+  int occ = 0;
+  KTF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+  if (occ < 1) occ = 1;
+  const long long ctas_needed = (a.total_groups + kWarpsPerCta - 1) / kWarpsPerCta;
+  const long long grid = std::min<long long>(ctas_needed, (long long)ktf::num_sms() * occ);
+  if (grid <= 0) return KTF_OK;
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
+  KTF_LAUNCH_OK();
+  return KTF_OK;
+}
+
+}  // namespace
+
+namespace ktf_fe {
+
+int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_host, const float* dct_host,
+              const float* lifter_host) {
+  const ktf_frontend_cfg& c = fe->cfg;
+  const int M = c.num_mels, Kc = c.num_ceps, C = 256;
+  const bool shape_ok = c.fft_length == 512 && c.frame_width == kW && (c.frame_shift % 4) == 0 &&
+                        c.frame_shift >= 4 && c.frame_shift <= 1024;
+  const bool kind_ok = (c.output == KTF_OUT_MFCC || c.output == KTF_OUT_FBANK) && c.use_power != 0;
+  if (!shape_ok || !kind_ok || mel_bank_host == nullptr || M < 1 || M > kMaxMels) return KTF_OK;
+  if (c.output == KTF_OUT_MFCC && (dct_host == nullptr || Kc < 1 || Kc > kMaxCeps)) return KTF_OK;
+  for (int i = 0; i < M; ++i)   // the fast path never computes the Nyquist bin
+    if (mel_bank_host[(size_t)C * M + i] != 0.0f) return KTF_OK;
+
+  // ---- mel filters: chunk ranges (4 bins), cut into units of 2 chunks, then a longest-first assignment of whole
+  //      filters to the 8 lanes of a frame ---------------------------------------------------------------------
+  struct Filt { int c0, n; };
+  std::vector<Filt> filt((size_t)M);
+  for (int i = 0; i < M; ++i) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < C; ++k)
+      if (mel_bank_host[(size_t)k * M + i] != 0.0f) { if (lo < 0) lo = k; hi = k; }
+    int c0 = 0, n = 0;
+    if (lo >= 0) { c0 = lo >> 2; n = (hi >> 2) - c0 + 1; }
+    filt[i] = {c0, n};
+  }
+  std::vector<int> order((size_t)M);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return filt[x].n > filt[y].n; });
+  std::vector<std::vector<int>> lanes(8);
+  int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i : order) {
+    int best = 0;
+    for (int l = 1; l < 8; ++l)
+      if (load[l] < load[best]) best = l;
+    lanes[best].push_back(i);
+    load[best] += (filt[i].n + 1) / 2;
+  }
+  int NU = 1;
+  for (int l = 0; l < 8; ++l) NU = std::max(NU, load[l]);
+
+  // Order of the filters inside each lane: at step u the 8 lanes of a frame read 8 different 4-bin chunks with one
+  // LDS.128; two chunks collide when they differ but are equal mod 8 (same banks).  A pairwise-swap local search
+  // minimises the number of extra wavefronts over the whole schedule; padding units read a free bank group.
+  auto unit_chunks = [&](int l, std::vector<int>& out) {
+    out.clear();
+    for (int i : lanes[l])
+      for (int cc = 0; cc < filt[i].n; cc += 2) out.push_back(filt[i].c0 + cc);
+  };
+  auto schedule_cost = [&]() {
+    std::vector<int> uc[8];
+    for (int l = 0; l < 8; ++l) unit_chunks(l, uc[l]);
+    int cost = 0;
+    for (int u = 0; u < NU; ++u) {
+      int worst = 1;
+      for (int g = 0; g < 8; ++g) {
+        int distinct[8], nd = 0;
+        for (int l = 0; l < 8; ++l) {
+          if (u >= (int)uc[l].size() || (uc[l][u] & 7) != g) continue;
+          bool seen = false;
+          for (int t = 0; t < nd; ++t) seen = seen || distinct[t] == uc[l][u];
+          if (!seen) distinct[nd++] = uc[l][u];
+        }
+        worst = std::max(worst, nd);
+      }
+      cost += worst - 1;
+    }
+    return cost;
+  };
+  {
+    int best = schedule_cost();
+    bool improved = best > 0;
+    for (int round = 0; round < 16 && improved; ++round) {
+      improved = false;
+      for (int l = 0; l < 8 && best > 0; ++l)
+        for (size_t x = 0; x < lanes[l].size(); ++x)
+          for (size_t y = x + 1; y < lanes[l].size(); ++y) {
+            std::swap(lanes[l][x], lanes[l][y]);
+            const int cst = schedule_cost();
+            if (cst < best) { best = cst; improved = true; } else std::swap(lanes[l][x], lanes[l][y]);
+          }
+    }
+  }
+
+  const int SD = pad4mod32(2 * (NU + 1)), SW = pad4mod32(8 * NU);
+  const int LMS = ((M + 3) & ~3) + 4;
+  const float one = 1.0f;
+  int one_bits;
+  memcpy(&one_bits, &one, sizeof(one_bits));
+  const int dct_floats = c.output == KTF_OUT_MFCC ? M * 32 : 0;
+  const int blob_floats = kOffUnits + 8 * SD + 8 * SW + dct_floats;
+  std::vector<float> blob((size_t)blob_floats, 0.0f);
+  for (int i = 0; i < kW; ++i) blob[kOffWin + i] = window_host[i];
+  for (int l = 0; l < 8; ++l) {
+    int* ud = reinterpret_cast<int*>(blob.data() + kOffUnits + l * SD);
+    float* uw = blob.data() + kOffUnits + 8 * SD + l * SW;
+    int u = 0;
+    for (int i : lanes[l])
+      for (int cc = 0; cc < filt[i].n; cc += 2, ++u) {
+        ud[2 * u] = (4 * (filt[i].c0 + cc)) | (i << 16);
+        ud[2 * u + 1] = (cc + 2 >= filt[i].n) ? 0 : one_bits;   // running sum restarts after the filter's last unit
+        for (int b8 = 0; b8 < 8; ++b8) {
+          const int k = 4 * (filt[i].c0 + cc) + b8;
+          const bool in = (cc + b8 / 4) < filt[i].n && k < C;
+          uw[8 * u + b8] = in ? mel_bank_host[(size_t)k * M + i] * 0.25f : 0.0f;   // the kernel stores 4|X|^2
+        }
+      }
+    // padding: zero weights, spare slot, chunk l (lane-distinct banks)
+    for (; u <= NU; ++u) { ud[2 * u] = (4 * l) | ((LMS - 1) << 16); ud[2 * u + 1] = 0; }
+  }
+
+  const double PI = 3.14159265358979323846;
+  for (int j = 0; j < 8; ++j)
+    for (int k1 = 0; k1 < 16; ++k1)
+      for (int h = 0; h < 2; ++h) {
+        const int n2 = 2 * j + h;
+        const double th = -2.0 * PI * (double)((n2 * k1) % 256) / 256.0;
+        blob[kOffTw1 + j * kTw1Stride + k1 * 4 + 2 * h] = (float)cos(th);
+        blob[kOffTw1 + j * kTw1Stride + k1 * 4 + 2 * h + 1] = (float)sin(th);
+      }
+  for (int j = 0; j < 8; ++j)
+    for (int e = 0; e < 16; ++e) {
+      int k = j + 16 * e;
+      if (j == 0) k = e < 8 ? 16 * e : 8 + 16 * e;
+      const double th = 2.0 * PI * (double)k / 512.0;   // -i * exp(-i th) = (-sin th, -cos th)
+      blob[kOffTw2 + j * kTw2Stride + e * 2] = (float)(-sin(th));
+      blob[kOffTw2 + j * kTw2Stride + e * 2 + 1] = (float)(-cos(th));
+    }
+  if (c.output == KTF_OUT_MFCC) {
+    float* dp = blob.data() + kOffUnits + 8 * SD + 8 * SW;
+    for (int i = 0; i < M; ++i)
+      for (int cc = 0; cc < Kc; ++cc) {
+        const float lf = (c.apply_lifter && lifter_host) ? lifter_host[cc] : 1.0f;
+        dp[(size_t)i * 32 + cc] = dct_host[(size_t)i * Kc + cc] * lf;
+      }
+  }
+
+  fe->r16_blob_floats = blob_floats;
+  fe->r16_nf = NU;
+  fe->r16_melw_floats = 8 * (SD + SW);
+  if (r16_smem_bytes(fe) > 227 * 1024) return KTF_OK;   // generic kernel instead
+  return ktf::upload(&fe->d_r16, blob.data(), blob.size());
+}
+
+int r16_launch(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
+  const bool raw = fe->cfg.raw_energy != 0;
+  if (fe->cfg.output == KTF_OUT_MFCC) {
+    if (fe->cfg.num_mels <= 32)
+      return raw ? launch_r16<KTF_OUT_MFCC, true, true>(fe, a, st) : launch_r16<KTF_OUT_MFCC, false, true>(fe, a, st);
+    return raw ? launch_r16<KTF_OUT_MFCC, true, false>(fe, a, st) : launch_r16<KTF_OUT_MFCC, false, false>(fe, a, st);
+  }
+  return raw ? launch_r16<KTF_OUT_FBANK, true, false>(fe, a, st) : launch_r16<KTF_OUT_FBANK, false, false>(fe, a, st);
+}
+
+}  // namespace ktf_fe
