@@ -670,6 +670,13 @@ int ktf_frontend_forward(const ktf_frontend* fe, const float* wav_dev, int64_t b
   a.groups_per_utt = (a.frames_per_utt + kFramesPerWarp - 1) / kFramesPerWarp;
   a.batch = batch;
   a.total_groups = a.groups_per_utt * batch;
+  // item / groups_per_utt as a multiply-shift: with m = ceil(2^40 / d), floor(n m / 2^40) == floor(n / d) whenever
+  // n (m d - 2^40) < 2^40, which holds for n d < 2^40; n m must also fit 64 bits (n < 2^23 d is implied)
+  a.div_magic = 0;
+  if (a.groups_per_utt > 0 && a.total_groups < (1ll << 31) &&
+      (double)a.total_groups * (double)a.groups_per_utt < 1.0e12 * 1.0995 &&
+      (double)a.total_groups * (double)(((1ull << 40) / (unsigned long long)a.groups_per_utt) + 1) < 1.8e19)
+    a.div_magic = ((1ull << 40) + (unsigned long long)a.groups_per_utt - 1) / (unsigned long long)a.groups_per_utt;
   cudaStream_t st = (cudaStream_t)stream;
   return dispatch(fe, a, st);
 }

@@ -29,6 +29,7 @@ struct FrontendArgs {
   const long long* group_offsets;
   long long batch;
   long long total_groups;
+  unsigned long long div_magic;   // ceil(2^40 / groups_per_utt) when item * groups_per_utt < 2^40 for every item, else 0
   // tables (global memory, copied to smem per CTA)
   const float* window;     // [W]
   const float2* stage_tw;  // [8][R+2]
@@ -73,7 +74,8 @@ __device__ __forceinline__ Item decode_item(const FrontendArgs& a, long long ite
   long long q, utt_frames;
   if (a.group_offsets == nullptr) {
     long long b;
-    if (a.total_groups < 0x7fffffffLL) b = (unsigned)item / (unsigned)a.groups_per_utt;   // 32-bit division
+    if (a.div_magic != 0) b = (long long)(((unsigned long long)item * a.div_magic) >> 40);   // exact, see fill site
+    else if (a.total_groups < 0x7fffffffLL) b = (unsigned)item / (unsigned)a.groups_per_utt;  // 32-bit division
     else b = item / a.groups_per_utt;
     q = item - b * a.groups_per_utt;
     it.utt_base = b * a.wav_stride;
@@ -106,7 +108,15 @@ __device__ __forceinline__ void stage_span(const FrontendArgs& a, const Item& it
   const unsigned sdst = (unsigned)__cvta_generic_to_shared(s_span);
   if (avail >= a.span && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0)) {
     const int n4 = a.span >> 2;
-    for (int i = lane; i < n4; i += 32) cp_async16(sdst + 16u * i, src + 4 * i);
+    if (n4 == 220) {   // 3 * 160 + 400 samples: the 16 kHz / 25 ms / 10 ms geometry, fully unrolled
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        const int i = lane + 32 * t;
+        if (t < 6 || i < 220) cp_async16(sdst + 16u * i, src + 4 * i);
+      }
+    } else {
+      for (int i = lane; i < n4; i += 32) cp_async16(sdst + 16u * i, src + 4 * i);
+    }
     for (int i = (n4 << 2) + lane; i < a.span; i += 32) cp_async4(sdst + 4u * i, src + i);
   } else {
     for (int i = lane; i < a.span; i += 32) {

@@ -76,16 +76,33 @@ __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d)
   d = make_float2(s1.x - s3.y, s1.y + s3.x);
 }
 
+// dft4 with d == 0 on input (x + 0 is not folded by the compiler: -0 + 0 = +0 under IEEE rules).
+__device__ __forceinline__ void dft4_d0(float2& a, float2& b, float2& c, float2& d) {
+  const float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = b;
+  a = cadd(s0, s2);
+  c = csub(s0, s2);
+  b = make_float2(s1.x + s2.y, s1.y - s2.x);
+  d = make_float2(s1.x - s2.y, s1.y + s2.x);
+}
+
 // 16-point complex FFT in registers (radix 4 x 4, decimation in frequency).  Input natural order,
 // output X[k] at x[pos16(k)].
 __host__ __device__ constexpr int pos16(int k) { return 4 * (k & 3) + (k >> 2); }
 
+// TAIL0: x[13], x[14], x[15] are zero on input (400-sample frames fill 13 of the 16 rows).
+template <bool TAIL0>
 __device__ __forceinline__ void fft16(float2 (&x)[16]) {
   // layer A: butterflies over (i, i+4, i+8, i+12); output q of butterfly i, times W_16^(i q), lands at 4q + i
   dft4(x[0], x[4], x[8], x[12]);
-  dft4(x[1], x[5], x[9], x[13]);
-  dft4(x[2], x[6], x[10], x[14]);
-  dft4(x[3], x[7], x[11], x[15]);
+  if constexpr (TAIL0) {
+    dft4_d0(x[1], x[5], x[9], x[13]);
+    dft4_d0(x[2], x[6], x[10], x[14]);
+    dft4_d0(x[3], x[7], x[11], x[15]);
+  } else {
+    dft4(x[1], x[5], x[9], x[13]);
+    dft4(x[2], x[6], x[10], x[14]);
+    dft4(x[3], x[7], x[11], x[15]);
+  }
   x[5] = mul_w16<1>(x[5]);   x[9] = mul_w16<2>(x[9]);   x[13] = mul_w16<3>(x[13]);
   x[6] = mul_w16<2>(x[6]);   x[10] = mul_w16<4>(x[10]); x[14] = mul_w16<6>(x[14]);
   x[7] = mul_w16<3>(x[7]);   x[11] = mul_w16<6>(x[11]); x[15] = mul_w16<9>(x[15]);
@@ -113,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
   float* s_warp0 = smem + a.r16_blob_floats;
 
   const int span_p = ((a.span + 3) & ~3) + 16;     // row 12 of the last frame reads 16 floats past the span
-  const int LMS = ((M + 3) & ~3) + 4;               // log-mel row stride (one spare slot for padding filters)
+  const int LMS = DCT_REG ? 36 : ((M + 3) & ~3) + 4;   // log-mel row stride (one spare slot for padding units)
   const int out_row = (OUTPUT == KTF_OUT_MFCC) ? a.Kc : M;
   const int out_sz = (4 * out_row + 3) & ~3;
   const int warp_floats = span_p + 4 * kTile + 4 * LMS + out_sz;
@@ -232,10 +249,10 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
     float4 t1[16];   // issued ahead of the FFTs so that their latency is covered by arithmetic
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) t1[k1] = tw1[k1];
-    fft16(ze);
+    fft16<true>(ze);
 #pragma unroll
     for (int k1 = 8; k1 < 16; ++k1) t1[k1] = tw1[k1];
-    fft16(zo);
+    fft16<true>(zo);
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
       float2 e = ze[pos16(k1)], o = zo[pos16(k1)];
@@ -263,8 +280,8 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
 #pragma unroll
     for (int e = 0; e < 8; ++e) t2[e] = tw2[e];
     __syncwarp();  // the tile is consumed; it is reused as the power buffer below
-    fft16(va);
-    fft16(vb);
+    fft16<false>(va);
+    fft16<false>(vb);
 
     // ---- real-FFT untangling + |X|^2 (x4; the 1/4 sits in the mel weights) ----------------------------------
     // evaluation e pairs zk = Z[k] with zp = Z[256 - k]:  4|X[k]|^2 = |S + G|^2, 4|X[256-k]|^2 = |S - G|^2,
@@ -430,10 +447,13 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
   }
 }
 
+__host__ int r16_lms(const ktf_frontend_cfg& c) {
+  return (c.output == KTF_OUT_MFCC && c.num_mels <= 32) ? 36 : ((c.num_mels + 3) & ~3) + 4;
+}
+
 size_t r16_smem_bytes(const ktf_frontend* fe) {
-  const int M = fe->cfg.num_mels;
   const int span_p = ((fe->span + 3) & ~3) + 16;
-  const int LMS = ((M + 3) & ~3) + 4;
+  const int LMS = r16_lms(fe->cfg);
   const int out_row = fe->out_dim;
   const int out_sz = (4 * out_row + 3) & ~3;
   const size_t warp_floats = (size_t)span_p + 4 * kTile + 4 * LMS + out_sz;
@@ -544,7 +564,7 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
   }
 
   const int SD = pad4mod32(2 * (NU + 1)), SW = pad4mod32(8 * NU);
-  const int LMS = ((M + 3) & ~3) + 4;
+  const int LMS = r16_lms(c);
   const float one = 1.0f;
   int one_bits;
   memcpy(&one_bits, &one, sizeof(one_bits));
