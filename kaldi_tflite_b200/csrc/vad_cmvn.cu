@@ -236,6 +236,120 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int dim, const long lo
   }
 }
 
+
+// Staged variant for utterances longer than the window: a CTA owns `tc` output frames of one utterance, copies the
+// tc + N - 1 input rows they depend on into shared memory with 16-byte asynchronous copies (one pass over HBM/L2,
+// every load in flight at once), and then slides the window out of shared memory.  The arithmetic (four partial sums
+// for the first window, add-new / subtract-old afterwards) is the one of cmvn_kernel.
+constexpr int kCmvnStagedWarps = 8;
+
+__global__ void __launch_bounds__(kCmvnStagedWarps * 32)
+cmvn_staged_kernel(const float* __restrict__ in, int dim, const long long* __restrict__ offs, int window,
+                   int norm_vars, int padding_valid, const long long* __restrict__ out_offs,
+                   float* __restrict__ out, int tc) {
+  extern __shared__ __align__(16) float sx[];
+  const long long b = blockIdx.x;
+  const long long r0 = offs[b];
+  const int T = (int)(offs[b + 1] - r0);
+  const int N = window;
+  int ta = 0, tb = T;
+  if (padding_valid) {
+    ta = N / 2;
+    tb = T - (N - 1) / 2;
+    if (tb < 0) tb += T;
+    if (tb < 0) tb = 0;
+    if (tb > T) tb = T;
+    if (ta > tb) ta = tb;
+  }
+  const long long o0 = out_offs ? out_offs[b] : r0;
+  const int c0 = ta + blockIdx.y * tc;
+  const int c1 = min(c0 + tc, tb);
+  if (c0 >= c1) return;
+  const float* x = in + r0 * dim;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (T <= N) {   // global statistics (cmvn.py:214-222): short utterances, read straight from global memory
+    const int per = (c1 - c0 + kCmvnStagedWarps - 1) / kCmvnStagedWarps;
+    const int t0 = c0 + warp * per, t1 = min(t0 + per, c1);
+    for (int d = lane; d < dim && t0 < t1; d += 32) {
+      float s = 0.0f, s2 = 0.0f;
+      for (int t = 0; t < T; ++t) {
+        const float v = x[(long long)t * dim + d];
+        s += v;
+        s2 += __fmul_rn(v, v);
+      }
+      const float mean = s / (float)T;
+      float sd = 1.0f;
+      if (norm_vars) sd = sqrtf(s2 / (float)T - __fmul_rn(mean, mean));
+      for (int t = t0; t < t1; ++t) {
+        float v = x[(long long)t * dim + d] - mean;
+        if (norm_vars) v = v / sd;
+        out[(o0 + (t - ta)) * dim + d] = v;
+      }
+    }
+    return;
+  }
+
+  // rows [lo, hi) cover every window of the CTA's frames (and the frames themselves)
+  const int lo = min(max(c0 - N / 2, 0), T - N);
+  const int hi = min(max(c1 - 1 - N / 2, 0), T - N) + N;
+  const float* src = x + (long long)lo * dim;
+  const int count = (hi - lo) * dim;
+  const int mis = (int)((reinterpret_cast<unsigned long long>(src) & 15ull) >> 2);   // floats past a 16-byte boundary
+  float* sbase = sx + mis;                                                            // same misalignment in smem
+  {
+    const int head = mis ? min(4 - mis, count) : 0;
+    for (int i = threadIdx.x; i < head; i += blockDim.x) sbase[i] = src[i];
+    const int body4 = (count - head) >> 2;
+    const unsigned sdst = (unsigned)__cvta_generic_to_shared(sbase + head);
+    const float* gsrc = src + head;
+    for (int i = threadIdx.x; i < body4; i += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst + 16u * i), "l"(gsrc + 4 * i) : "memory");
+    for (int i = head + (body4 << 2) + threadIdx.x; i < count; i += blockDim.x) sbase[i] = src[i];
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  const int per = (c1 - c0 + kCmvnStagedWarps - 1) / kCmvnStagedWarps;
+  const int t0 = c0 + warp * per, t1 = min(t0 + per, c1);
+  if (t0 >= t1) return;
+  const float* xs = sbase - (long long)lo * dim;   // xs[t * dim + d] == x[t * dim + d] for lo <= t < hi
+  const float inv_n = 1.0f / (float)N;
+  for (int d = lane; d < dim; d += 32) {
+    int ws = min(max(t0 - N / 2, 0), T - N);
+    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+    int t = ws;
+    for (; t + 4 <= ws + N; t += 4) {
+      const float v0 = xs[t * dim + d], v1 = xs[(t + 1) * dim + d];
+      const float v2 = xs[(t + 2) * dim + d], v3 = xs[(t + 3) * dim + d];
+      p0 += v0; p1 += v1; p2 += v2; p3 += v3;
+      q0 += __fmul_rn(v0, v0); q1 += __fmul_rn(v1, v1); q2 += __fmul_rn(v2, v2); q3 += __fmul_rn(v3, v3);
+    }
+    for (; t < ws + N; ++t) {
+      const float v = xs[t * dim + d];
+      p0 += v;
+      q0 += __fmul_rn(v, v);
+    }
+    float s = (p0 + p1) + (p2 + p3), s2 = (q0 + q1) + (q2 + q3);
+#pragma unroll 4
+    for (int tt = t0; tt < t1; ++tt) {
+      const int want = min(max(tt - N / 2, 0), T - N);
+      const float xc = xs[tt * dim + d];
+      if (want != ws) {  // advances by exactly one
+        const float vo = xs[ws * dim + d];
+        const float vn = xs[(ws + N) * dim + d];
+        s += vn - vo;
+        s2 += __fmul_rn(vn, vn) - __fmul_rn(vo, vo);
+        ws = want;
+      }
+      const float mean = s * inv_n;
+      float v = xc - mean;
+      if (norm_vars) v = v / sqrtf(s2 * inv_n - __fmul_rn(mean, mean));
+      out[(o0 + (tt - ta)) * dim + d] = v;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -294,6 +408,24 @@ int ktf_cmvn_forward(const float* in_dev, int32_t dim, const int64_t* frame_offs
   KTF_CHECK_ARG(window > 0, "`window` and `min_window` must be > 0");
   KTF_CHECK_ARG(!padding_valid || out_offsets_dev, "out_offsets_dev is required for VALID padding");
   if (batch <= 0 || total_frames <= 0 || max_frames <= 0) return KTF_OK;
+  {
+    // staged kernel when a CTA's rows fit in shared memory with >= 2 CTAs per SM
+    const int tc = 256;
+    const size_t smem = ((size_t)(tc + window) * dim + 4) * sizeof(float);
+    const long long gys = (max_frames + tc - 1) / tc;
+    if (smem <= 113 * 1024 && gys <= 65535) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        KTF_CUDA(cudaFuncSetAttribute(cmvn_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        attr_set = true;
+      }
+      cmvn_staged_kernel<<<dim3((unsigned)batch, (unsigned)gys), kCmvnStagedWarps * 32, smem, (cudaStream_t)stream>>>(
+          in_dev, dim, (const long long*)frame_offsets_dev, window, norm_vars, padding_valid,
+          (const long long*)out_offsets_dev, out_dev, tc);
+      KTF_LAUNCH_OK();
+      return KTF_OK;
+    }
+  }
   const long long per_block = (long long)kCmvnY * kCmvnSub;
   const long long gy = (max_frames + per_block - 1) / per_block;
   KTF_CHECK_ARG(gy <= 65535, "max_frames too large for ktf_cmvn_forward");
