@@ -610,7 +610,7 @@ def roofline_for(workload, r, pk):
         achieved = ALGO_BYTES_PER_UTT * BATCH / (r["kernel_ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
                 "traffic": None, "peak_source": pk["src"] + " hbm_gbs",
-                "kernel": "frontend_kernel (framing+window+FFT+mel+log+DCT)", "kernel_ms": r["kernel_ms"],
+                "kernel": "frontend_r16_kernel (framing+window+FFT+mel+log+DCT)", "kernel_ms": r["kernel_ms"],
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UTT * BATCH}
         tf = os.path.join(ROOT, "profiles", "frontend_traffic.json")
         if os.path.exists(tf):

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Round profile set (run under gpurun): bench line, ncu launch list of the same command, full captures of the
+# front-end and CMVN kernels at the bench workload.  $1 = tag
+TAG=${1:-r01}
+mkdir -p gpurun_out
+python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 1 > gpurun_out/bench_under_ncu_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:frontend_r16 -s 3 -c 1 \
+    -o gpurun_out/prof_fe_$TAG -f python scripts/quick_time.py 1024 > gpurun_out/ncu_fe_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:cmvn_staged -s 3 -c 1 \
+    -o gpurun_out/prof_cmvn_$TAG -f python scripts/quick_time.py 1024 > gpurun_out/ncu_cmvn_$TAG.log 2>&1
+cat gpurun_out/bench_$TAG.json

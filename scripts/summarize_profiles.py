@@ -21,6 +21,7 @@ KEYS = [
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
 ]
