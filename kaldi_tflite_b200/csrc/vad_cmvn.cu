@@ -243,10 +243,12 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int dim, const long lo
 // for the first window, add-new / subtract-old afterwards) is the one of cmvn_kernel.
 constexpr int kCmvnStagedWarps = 8;
 
+template <bool NORM_VARS>
 __global__ void __launch_bounds__(kCmvnStagedWarps * 32)
 cmvn_staged_kernel(const float* __restrict__ in, int dim, const long long* __restrict__ offs, int window,
-                   int norm_vars, int padding_valid, const long long* __restrict__ out_offs,
+                   int padding_valid, const long long* __restrict__ out_offs,
                    float* __restrict__ out, int tc) {
+  constexpr int norm_vars = NORM_VARS ? 1 : 0;
   extern __shared__ __align__(16) float sx[];
   const long long b = blockIdx.x;
   const long long r0 = offs[b];
@@ -315,38 +317,58 @@ cmvn_staged_kernel(const float* __restrict__ in, int dim, const long long* __res
   if (t0 >= t1) return;
   const float* xs = sbase - (long long)lo * dim;   // xs[t * dim + d] == x[t * dim + d] for lo <= t < hi
   const float inv_n = 1.0f / (float)N;
+  const int H = N / 2;
   for (int d = lane; d < dim; d += 32) {
-    int ws = min(max(t0 - N / 2, 0), T - N);
+    int ws = min(max(t0 - H, 0), T - N);
     float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
-    int t = ws;
-    for (; t + 4 <= ws + N; t += 4) {
-      const float v0 = xs[t * dim + d], v1 = xs[(t + 1) * dim + d];
-      const float v2 = xs[(t + 2) * dim + d], v3 = xs[(t + 3) * dim + d];
-      p0 += v0; p1 += v1; p2 += v2; p3 += v3;
-      q0 += __fmul_rn(v0, v0); q1 += __fmul_rn(v1, v1); q2 += __fmul_rn(v2, v2); q3 += __fmul_rn(v3, v3);
-    }
-    for (; t < ws + N; ++t) {
-      const float v = xs[t * dim + d];
-      p0 += v;
-      q0 += __fmul_rn(v, v);
+    {
+      const float* col = xs + ws * dim + d;
+      int k = 0;
+      for (; k + 4 <= N; k += 4) {
+        const float v0 = col[k * dim], v1 = col[(k + 1) * dim], v2 = col[(k + 2) * dim], v3 = col[(k + 3) * dim];
+        p0 += v0; p1 += v1; p2 += v2; p3 += v3;
+        if (NORM_VARS) {
+          q0 += __fmul_rn(v0, v0); q1 += __fmul_rn(v1, v1); q2 += __fmul_rn(v2, v2); q3 += __fmul_rn(v3, v3);
+        }
+      }
+      for (; k < N; ++k) {
+        const float v = col[k * dim];
+        p0 += v;
+        if (NORM_VARS) q0 += __fmul_rn(v, v);
+      }
     }
     float s = (p0 + p1) + (p2 + p3), s2 = (q0 + q1) + (q2 + q3);
-#pragma unroll 4
-    for (int tt = t0; tt < t1; ++tt) {
-      const int want = min(max(tt - N / 2, 0), T - N);
-      const float xc = xs[tt * dim + d];
-      if (want != ws) {  // advances by exactly one
-        const float vo = xs[ws * dim + d];
-        const float vn = xs[(ws + N) * dim + d];
-        s += vn - vo;
-        s2 += __fmul_rn(vn, vn) - __fmul_rn(vo, vo);
-        ws = want;
-      }
+    float* orow = out + (o0 + (t0 - ta)) * dim + d;
+    int tt = t0;
+    auto emit = [&](int t_) {
       const float mean = s * inv_n;
-      float v = xc - mean;
-      if (norm_vars) v = v / sqrtf(s2 * inv_n - __fmul_rn(mean, mean));
-      out[(o0 + (tt - ta)) * dim + d] = v;
+      float v = xs[t_ * dim + d] - mean;
+      if (NORM_VARS) v = v / sqrtf(s2 * inv_n - __fmul_rn(mean, mean));
+      *orow = v;
+      orow += dim;
+    };
+    // head: frames whose window is still clamped at the start of the utterance (ws == 0)
+    for (; tt < t1 && tt - H <= ws; ++tt) emit(tt);
+    // interior: the window advances by exactly one row per frame
+    const int t_mid = min(t1, T - N + H + 1);   // last frame + 1 with an unclamped window start
+    const float* po = xs + ws * dim + d;        // row leaving the window
+    const float* pn = po + N * dim;             // row entering it
+    const float* px = xs + tt * dim + d;
+#pragma unroll 4
+    for (; tt < t_mid; ++tt) {
+      const float vo = *po, vn = *pn;
+      s += vn - vo;
+      if (NORM_VARS) s2 += __fmul_rn(vn, vn) - __fmul_rn(vo, vo);
+      po += dim; pn += dim;
+      const float mean = s * inv_n;
+      float v = *px - mean;
+      px += dim;
+      if (NORM_VARS) v = v / sqrtf(s2 * inv_n - __fmul_rn(mean, mean));
+      *orow = v;
+      orow += dim;
     }
+    // tail: window clamped at the end of the utterance
+    for (; tt < t1; ++tt) emit(tt);
   }
 }
 
@@ -416,11 +438,13 @@ int ktf_cmvn_forward(const float* in_dev, int32_t dim, const int64_t* frame_offs
     if (smem <= 113 * 1024 && gys <= 65535) {
       static bool attr_set = false;
       if (!attr_set) {
-        KTF_CUDA(cudaFuncSetAttribute(cmvn_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        KTF_CUDA(cudaFuncSetAttribute(cmvn_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        KTF_CUDA(cudaFuncSetAttribute(cmvn_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
         attr_set = true;
       }
-      cmvn_staged_kernel<<<dim3((unsigned)batch, (unsigned)gys), kCmvnStagedWarps * 32, smem, (cudaStream_t)stream>>>(
-          in_dev, dim, (const long long*)frame_offsets_dev, window, norm_vars, padding_valid,
+      auto kern = norm_vars ? cmvn_staged_kernel<true> : cmvn_staged_kernel<false>;
+      kern<<<dim3((unsigned)batch, (unsigned)gys), kCmvnStagedWarps * 32, smem, (cudaStream_t)stream>>>(
+          in_dev, dim, (const long long*)frame_offsets_dev, window, padding_valid,
           (const long long*)out_offsets_dev, out_dev, tc);
       KTF_LAUNCH_OK();
       return KTF_OK;
