@@ -103,6 +103,26 @@ int ktf_frontend_forward_ragged(const ktf_frontend* fe, const float* wav_dev, in
                                 const int64_t* sample_offsets_host, int64_t* frame_offsets_host,
                                 float* out_dev, float* energy_dev, void* stream);
 
+/* Ingest options of the step BEFORE the reference path:
+ *   sample_format  KTF_SAMPLE_F32: float32 samples in int16 scale (the reference's input convention,
+ *                  models/kaldi/xvector_extractor.py:90-91); KTF_SAMPLE_S16: raw int16 PCM as stored in a wav file --
+ *                  replaces the loaders' int16 -> float32 step (testdata/feats/feats.py:31-34) and halves the bytes
+ *                  that cross PCIe and HBM.  int16 needs the fused 400-sample / 512-point MFCC / fbank kernel.
+ *   snip_edges     1: frames as in framing.py:231-239 (no padding).  0: Kaldi's default snip-edges=false -- the
+ *                  utterance is mirror-padded on both sides INSIDE the kernel (index reflection while staging), which
+ *                  replaces kaldi_numpy.PadWaveform (kaldi_numpy/frame_extraction.py:54-89) on the host;
+ *                  (num_samples + shift/2) / shift frames.
+ * ktf_frontend_forward / _ragged are the (F32, snip_edges=1) special cases. */
+enum { KTF_SAMPLE_F32 = 0, KTF_SAMPLE_S16 = 1 };
+int64_t ktf_frontend_num_frames_ex(const ktf_frontend* fe, int64_t num_samples, int32_t snip_edges);
+int ktf_frontend_forward_ex(const ktf_frontend* fe, const void* wav_dev, int32_t sample_format,
+                            int32_t snip_edges, int64_t batch, int64_t num_samples, int64_t wav_stride,
+                            float* out_dev, float* energy_dev, void* stream);
+int ktf_frontend_forward_ragged_ex(const ktf_frontend* fe, const void* wav_dev, int32_t sample_format,
+                                   int32_t snip_edges, int64_t batch, const int64_t* sample_offsets_host,
+                                   int64_t* frame_offsets_host, float* out_dev, float* energy_dev,
+                                   void* stream);
+
 /* Framing alone (only when a caller really wants frames in HBM): out (batch, T, frame_width). */
 int ktf_framing_forward(const float* wav_dev, int64_t batch, int64_t num_samples,
                         int64_t wav_stride, int32_t frame_width, int32_t frame_shift,

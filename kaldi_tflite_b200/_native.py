@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libktf_b200.so")
 
 KTF_OUT_MFCC, KTF_OUT_FBANK, KTF_OUT_WINDOWED = 0, 1, 2
+KTF_SAMPLE_F32, KTF_SAMPLE_S16 = 0, 1
 KTF_PREC_F32, KTF_PREC_BF16 = 0, 1
 KTF_ACT_NONE, KTF_ACT_RELU = 0, 1
 KTF_MAX_CONTEXT = 16
@@ -56,6 +57,9 @@ _SIGNATURES = {
     "ktf_frontend_out_dim": (c_int32, [_P]),
     "ktf_frontend_forward": (c_int32, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P]),
     "ktf_frontend_forward_ragged": (c_int32, [_P, _P, c_int64, _P, _P, _P, _P, _P]),
+    "ktf_frontend_num_frames_ex": (c_int64, [_P, c_int64, c_int32]),
+    "ktf_frontend_forward_ex": (c_int32, [_P, _P, c_int32, c_int32, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "ktf_frontend_forward_ragged_ex": (c_int32, [_P, _P, c_int32, c_int32, c_int64, _P, _P, _P, _P, _P]),
     "ktf_framing_forward": (c_int32, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, _P, _P]),
     "ktf_vad_mask": (c_int32, [POINTER(VadCfg), _P, c_int32, _P, c_int64, c_int64, _P, _P]),
     "ktf_vad_compact_workspace": (c_int64, [c_int64, c_int64]),

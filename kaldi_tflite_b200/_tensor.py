@@ -34,6 +34,12 @@ def as_device(x, dtype=torch.float32):
     return t.to(device=device(), dtype=dtype, non_blocking=True).contiguous()
 
 
+def is_int16(x):
+    """True for numpy / torch int16 arrays: raw PCM that stays 16-bit up to the front-end kernel."""
+    dt = getattr(x, "dtype", None)
+    return dt is torch.int16 or (isinstance(dt, np.dtype) and dt == np.int16)
+
+
 def ptr(t):
     if t is None:
         return ctypes.c_void_p(0)

@@ -643,16 +643,42 @@ void ktf_frontend_destroy(ktf_frontend* fe) {
   delete fe;
 }
 
-int64_t ktf_frontend_num_frames(const ktf_frontend* fe, int64_t num_samples) {
+int64_t ktf_frontend_num_frames_ex(const ktf_frontend* fe, int64_t num_samples, int32_t snip_edges) {
   if (!fe || num_samples < fe->cfg.frame_width) return 0;
-  return 1 + (num_samples - fe->cfg.frame_width) / fe->cfg.frame_shift;
+  if (snip_edges) return 1 + (num_samples - fe->cfg.frame_width) / fe->cfg.frame_shift;
+  return (num_samples + fe->cfg.frame_shift / 2) / fe->cfg.frame_shift;   // kaldi_numpy/frame_extraction.py:78-80
+}
+
+int64_t ktf_frontend_num_frames(const ktf_frontend* fe, int64_t num_samples) {
+  return ktf_frontend_num_frames_ex(fe, num_samples, 1);
 }
 
 int32_t ktf_frontend_out_dim(const ktf_frontend* fe) { return fe ? fe->out_dim : 0; }
 
-int ktf_frontend_forward(const ktf_frontend* fe, const float* wav_dev, int64_t batch,
-                         int64_t num_samples, int64_t wav_stride, float* out_dev,
-                         float* energy_dev, void* stream) {
+namespace {
+
+// Common argument checks / setup of the ingest options (sample format, snip-edges).
+int set_ingest(const ktf_frontend* fe, FrontendArgs& a, const void* wav_dev, int32_t sample_format,
+               int32_t snip_edges) {
+  KTF_CHECK_ARG(sample_format == KTF_SAMPLE_F32 || sample_format == KTF_SAMPLE_S16, "unknown sample_format %d",
+                sample_format);
+  if (sample_format == KTF_SAMPLE_S16) {
+    KTF_CHECK_ARG(fe->d_r16 != nullptr,
+                  "int16 input is implemented by the fused 400-sample / 512-point MFCC / fbank kernel only");
+    a.wav16 = static_cast<const short*>(wav_dev);
+  } else {
+    a.wav = static_cast<const float*>(wav_dev);
+  }
+  a.edge_off = snip_edges ? 0 : (fe->cfg.frame_width - fe->cfg.frame_shift) / 2;   // frame_extraction.py:85
+  KTF_CHECK_ARG(a.edge_off >= 0, "snip_edges=0 needs frame_width >= frame_shift");
+  return KTF_OK;
+}
+
+}  // namespace
+
+int ktf_frontend_forward_ex(const ktf_frontend* fe, const void* wav_dev, int32_t sample_format,
+                            int32_t snip_edges, int64_t batch, int64_t num_samples, int64_t wav_stride,
+                            float* out_dev, float* energy_dev, void* stream) {
   KTF_CHECK_ARG(fe && wav_dev && out_dev, "ktf_frontend_forward: null argument");
   KTF_CHECK_ARG(batch >= 0 && wav_stride >= num_samples, "bad batch / stride");
   KTF_CHECK_ARG(num_samples >= fe->cfg.frame_width,
@@ -661,17 +687,18 @@ int ktf_frontend_forward(const ktf_frontend* fe, const float* wav_dev, int64_t b
   if (batch == 0) return KTF_OK;
   FrontendArgs a{};
   fill_args(fe, a);
-  a.wav = wav_dev;
+  int rc = set_ingest(fe, a, wav_dev, sample_format, snip_edges);
+  if (rc != KTF_OK) return rc;
   a.out = out_dev;
   a.energy_out = energy_dev;
   a.wav_stride = wav_stride;
   a.num_samples = num_samples;
-  a.frames_per_utt = ktf_frontend_num_frames(fe, num_samples);
+  a.frames_per_utt = ktf_frontend_num_frames_ex(fe, num_samples, snip_edges);
   a.groups_per_utt = (a.frames_per_utt + kFramesPerWarp - 1) / kFramesPerWarp;
   a.batch = batch;
   a.total_groups = a.groups_per_utt * batch;
   // item / groups_per_utt as a multiply-shift: with m = ceil(2^40 / d), floor(n m / 2^40) == floor(n / d) whenever
-  // n (m d - 2^40) < 2^40, which holds for n d < 2^40; n m must also fit 64 bits (n < 2^23 d is implied)
+  // n (m d - 2^40) < 2^40, which holds for n d < 2^40; n m must also fit 64 bits
   a.div_magic = 0;
   if (a.groups_per_utt > 0 && a.total_groups < (1ll << 31) &&
       (double)a.total_groups * (double)a.groups_per_utt < 1.0e12 * 1.0995 &&
@@ -681,9 +708,17 @@ int ktf_frontend_forward(const ktf_frontend* fe, const float* wav_dev, int64_t b
   return dispatch(fe, a, st);
 }
 
-int ktf_frontend_forward_ragged(const ktf_frontend* fe, const float* wav_dev, int64_t batch,
-                                const int64_t* sample_offsets_host, int64_t* frame_offsets_host,
-                                float* out_dev, float* energy_dev, void* stream) {
+int ktf_frontend_forward(const ktf_frontend* fe, const float* wav_dev, int64_t batch,
+                         int64_t num_samples, int64_t wav_stride, float* out_dev,
+                         float* energy_dev, void* stream) {
+  return ktf_frontend_forward_ex(fe, wav_dev, KTF_SAMPLE_F32, 1, batch, num_samples, wav_stride, out_dev,
+                                 energy_dev, stream);
+}
+
+int ktf_frontend_forward_ragged_ex(const ktf_frontend* fe, const void* wav_dev, int32_t sample_format,
+                                   int32_t snip_edges, int64_t batch, const int64_t* sample_offsets_host,
+                                   int64_t* frame_offsets_host, float* out_dev, float* energy_dev,
+                                   void* stream) {
   KTF_CHECK_ARG(fe && wav_dev && out_dev && sample_offsets_host && frame_offsets_host,
                 "ktf_frontend_forward_ragged: null argument");
   if (batch <= 0) return KTF_OK;
@@ -700,21 +735,23 @@ int ktf_frontend_forward_ragged(const ktf_frontend* fe, const float* wav_dev, in
     KTF_CHECK_ARG(len >= fe->cfg.frame_width,
                   "utterance %lld: input sample size (%lld) must be >= frame size (%d)",
                   (long long)b, (long long)len, fe->cfg.frame_width);
-    const int64_t T = ktf_frontend_num_frames(fe, len);
+    const int64_t T = ktf_frontend_num_frames_ex(fe, len, snip_edges);
     fo[b + 1] = fo[b] + T;
     go[b + 1] = go[b] + (T + kFramesPerWarp - 1) / kFramesPerWarp;
   }
   so[batch] = sample_offsets_host[batch];
   for (int64_t b = 0; b <= batch; ++b) frame_offsets_host[b] = fo[b];
 
+  FrontendArgs a{};
+  fill_args(fe, a);
+  int rc = set_ingest(fe, a, wav_dev, sample_format, snip_edges);
+  if (rc != KTF_OK) return rc;
+
   long long* dev = nullptr;
   KTF_CUDA(ktf::malloc_async((void**)&dev, host.size() * sizeof(long long), st));
   KTF_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
   KTF_CUDA(cudaStreamSynchronize(st));  // `host` is pageable and dies at return
 
-  FrontendArgs a{};
-  fill_args(fe, a);
-  a.wav = wav_dev;
   a.out = out_dev;
   a.energy_out = energy_dev;
   a.sample_offsets = dev;
@@ -722,9 +759,16 @@ int ktf_frontend_forward_ragged(const ktf_frontend* fe, const float* wav_dev, in
   a.group_offsets = dev + 2 * (batch + 1);
   a.batch = batch;
   a.total_groups = go[batch];
-  int rc = dispatch(fe, a, st);
+  rc = dispatch(fe, a, st);
   cudaFreeAsync(dev, st);
   return rc;
+}
+
+int ktf_frontend_forward_ragged(const ktf_frontend* fe, const float* wav_dev, int64_t batch,
+                                const int64_t* sample_offsets_host, int64_t* frame_offsets_host,
+                                float* out_dev, float* energy_dev, void* stream) {
+  return ktf_frontend_forward_ragged_ex(fe, wav_dev, KTF_SAMPLE_F32, 1, batch, sample_offsets_host,
+                                        frame_offsets_host, out_dev, energy_dev, stream);
 }
 
 int ktf_framing_forward(const float* wav_dev, int64_t batch, int64_t num_samples,

@@ -15,7 +15,8 @@ constexpr int kGroups = 8;  // the 8 lanes of a frame cooperate as 8 "groups" in
 
 struct FrontendArgs {
   // data
-  const float* wav;
+  const float* wav;       // float32 samples, or
+  const short* wav16;     // int16 PCM samples (fast path only); exactly one of the two is non-null
   float* out;
   float* energy_out;
   // uniform batch
@@ -29,6 +30,7 @@ struct FrontendArgs {
   const long long* group_offsets;
   long long batch;
   long long total_groups;
+  int edge_off;           // samples the first frame starts before sample 0 (0 = snip-edges, else mirror padding)
   unsigned long long div_magic;   // ceil(2^40 / groups_per_utt) when item * groups_per_utt < 2^40 for every item, else 0
   // tables (global memory, copied to smem per CTA)
   const float* window;     // [W]
@@ -99,14 +101,23 @@ __device__ __forceinline__ Item decode_item(const FrontendArgs& a, long long ite
   return it;
 }
 
-// Asynchronously stages the item's sample span into the warp's smem buffer (zero filled past the
-// end of the utterance).  16-byte copies when source and length allow, 4-byte copies otherwise.
+// Source sample index of position `idx` of the (virtually) mirror-padded utterance: Kaldi's snip-edges=false
+// reflection (kaldi_numpy/frame_extraction.py:28-51), clamped for utterances shorter than the padding.
+__device__ __forceinline__ long long reflect_index(long long idx, long long len) {
+  if (idx < 0) idx = -idx - 1;
+  if (idx >= len) idx = 2 * len - 1 - idx;
+  return idx < 0 ? 0 : (idx >= len ? len - 1 : idx);
+}
+
+// Asynchronously stages the item's sample span into the warp's smem buffer.  16-byte copies when the span is inside
+// the utterance and aligned; otherwise element copies, zero filled past the end of the utterance (snip-edges) or
+// mirrored at both ends (edge_off > 0).
 __device__ __forceinline__ void stage_span(const FrontendArgs& a, const Item& it, float* s_span, int lane) {
-  const long long s0 = it.frame0 * a.shift;
+  const long long s0 = it.frame0 * a.shift - a.edge_off;
   const float* src = a.wav + it.utt_base + s0;
   const long long avail = it.utt_len - s0;
   const unsigned sdst = (unsigned)__cvta_generic_to_shared(s_span);
-  if (avail >= a.span && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0)) {
+  if (s0 >= 0 && avail >= a.span && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0)) {
     const int n4 = a.span >> 2;
     if (n4 == 220) {   // 3 * 160 + 400 samples: the 16 kHz / 25 ms / 10 ms geometry, fully unrolled
 #pragma unroll
@@ -118,10 +129,31 @@ __device__ __forceinline__ void stage_span(const FrontendArgs& a, const Item& it
       for (int i = lane; i < n4; i += 32) cp_async16(sdst + 16u * i, src + 4 * i);
     }
     for (int i = (n4 << 2) + lane; i < a.span; i += 32) cp_async4(sdst + 4u * i, src + i);
-  } else {
+  } else if (a.edge_off == 0) {
     for (int i = lane; i < a.span; i += 32) {
       if (i < avail) cp_async4(sdst + 4u * i, src + i); else s_span[i] = 0.0f;
     }
+  } else {
+    const float* utt = a.wav + it.utt_base;
+    for (int i = lane; i < a.span; i += 32) cp_async4(sdst + 4u * i, utt + reflect_index(s0 + i, it.utt_len));
+  }
+}
+
+// int16 PCM variant: the smem buffer holds the raw 16-bit samples (converted when the window is applied).
+__device__ __forceinline__ void stage_span16(const FrontendArgs& a, const Item& it, short* s_span, int lane) {
+  const long long s0 = it.frame0 * a.shift - a.edge_off;
+  const short* src = a.wav16 + it.utt_base + s0;
+  const long long avail = it.utt_len - s0;
+  const unsigned sdst = (unsigned)__cvta_generic_to_shared(s_span);
+  if (s0 >= 0 && avail >= a.span && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0) && (a.span & 7) == 0) {
+    const int n8 = a.span >> 3;
+    for (int i = lane; i < n8; i += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst + 16u * i), "l"(src + 8 * i) : "memory");
+  } else if (a.edge_off == 0) {
+    for (int i = lane; i < a.span; i += 32) s_span[i] = (i < avail) ? src[i] : (short)0;
+  } else {
+    const short* utt = a.wav16 + it.utt_base;
+    for (int i = lane; i < a.span; i += 32) s_span[i] = utt[reflect_index(s0 + i, it.utt_len)];
   }
 }
 

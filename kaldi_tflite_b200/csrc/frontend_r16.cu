@@ -115,7 +115,9 @@ __device__ __forceinline__ void fft16(float2 (&x)[16]) {
 
 // DCT_REG (MFCC with <= 32 mel bins): lane c keeps column c of the DCT matrix in registers and produces cepstrum
 // c of all 4 frames, so the DCT reads no table at all (only broadcast loads of the log-mel rows).
-template <int OUTPUT, bool RAW_ENERGY, bool DCT_REG>
+// PCM16: the input is int16 PCM; the span buffer holds the raw 16-bit samples (half the HBM / L2 / smem bytes) and
+// they are converted when the window is applied.
+template <int OUTPUT, bool RAW_ENERGY, bool DCT_REG, bool PCM16>
 __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const FrontendArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int NU = a.r16_nf;                        // mel units (8 bins each) per lane
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
   long long item = warp_global;
   if (item < a.total_groups) {
     cur = decode_item(a, item);
-    stage_span(a, cur, s_span, lane);
+    if (PCM16) stage_span16(a, cur, reinterpret_cast<short*>(s_span), lane); else stage_span(a, cur, s_span, lane);
   }
   for (int i = threadIdx.x; i < a.r16_blob_floats; i += kThreads) smem[i] = a.r16_blob[i];
   for (int i = lane; i < 4 * LMS; i += 32) s_LM[i] = 0.0f;   // slots >= M stay finite
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
 
   // per-lane bases: everything below is base + immediate
   const float* fr = s_span + f * a.shift + 4 * j;
+  const short* fr16 = reinterpret_cast<const short*>(s_span) + f * a.shift + 4 * j;
   const float* wn = s_win + 4 * j;
   const float4* tw1 = s_tw1 + j * (kTw1Stride / 4);
   const float4* tw2 = s_tw2 + j * (kTw2Stride / 4);
@@ -198,7 +201,13 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
       float sum = 0.0f;
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
-        xv[r] = *reinterpret_cast<const float4*>(fr + 32 * r);
+        if (PCM16) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(fr16 + 32 * r);
+          xv[r] = make_float4((float)(short)(raw.x & 0xffffu), (float)(short)(raw.x >> 16),
+                              (float)(short)(raw.y & 0xffffu), (float)(short)(raw.y >> 16));
+        } else {
+          xv[r] = *reinterpret_cast<const float4*>(fr + 32 * r);
+        }
         if (r == kRows - 1 && !tail_ok) xv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         // sample 32r + 4j - 1 is the last of the previous lane's four (lane 0: lane 7's four of the previous row)
         const float give = (r > 0 && j == 7) ? xv[r - 1].w : xv[r].w;
@@ -234,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
       const long long nxt = item + warp_stride;
       if (nxt < a.total_groups) {
         cur = decode_item(a, nxt);
-        stage_span(a, cur, s_span, lane);
+        if (PCM16) stage_span16(a, cur, reinterpret_cast<short*>(s_span), lane); else stage_span(a, cur, s_span, lane);
       }
     }
 
@@ -460,10 +469,10 @@ size_t r16_smem_bytes(const ktf_frontend* fe) {
   return ((size_t)fe->r16_blob_floats + kWarpsPerCta * warp_floats) * sizeof(float);
 }
 
-template <int OUTPUT, bool RAW, bool DCT_REG>
+template <int OUTPUT, bool RAW, bool DCT_REG, bool PCM16>
 int launch_r16(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
   const size_t smem = r16_smem_bytes(fe);
-  auto kern = frontend_r16_kernel<OUTPUT, RAW, DCT_REG>;
+  auto kern = frontend_r16_kernel<OUTPUT, RAW, DCT_REG, PCM16>;
   KTF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)std::max<size_t>(smem, 48 * 1024)));
   int occ = 0;
@@ -623,14 +632,19 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
   return ktf::upload(&fe->d_r16, blob.data(), blob.size());
 }
 
+template <int OUTPUT, bool DCT_REG>
+int launch_r16_sel(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
+  const bool raw = fe->cfg.raw_energy != 0, pcm = a.wav16 != nullptr;
+  if (raw) return pcm ? launch_r16<OUTPUT, true, DCT_REG, true>(fe, a, st) : launch_r16<OUTPUT, true, DCT_REG, false>(fe, a, st);
+  return pcm ? launch_r16<OUTPUT, false, DCT_REG, true>(fe, a, st) : launch_r16<OUTPUT, false, DCT_REG, false>(fe, a, st);
+}
+
 int r16_launch(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
-  const bool raw = fe->cfg.raw_energy != 0;
   if (fe->cfg.output == KTF_OUT_MFCC) {
-    if (fe->cfg.num_mels <= 32)
-      return raw ? launch_r16<KTF_OUT_MFCC, true, true>(fe, a, st) : launch_r16<KTF_OUT_MFCC, false, true>(fe, a, st);
-    return raw ? launch_r16<KTF_OUT_MFCC, true, false>(fe, a, st) : launch_r16<KTF_OUT_MFCC, false, false>(fe, a, st);
+    if (fe->cfg.num_mels <= 32) return launch_r16_sel<KTF_OUT_MFCC, true>(fe, a, st);
+    return launch_r16_sel<KTF_OUT_MFCC, false>(fe, a, st);
   }
-  return raw ? launch_r16<KTF_OUT_FBANK, true, false>(fe, a, st) : launch_r16<KTF_OUT_FBANK, false, false>(fe, a, st);
+  return launch_r16_sel<KTF_OUT_FBANK, false>(fe, a, st);
 }
 
 }  // namespace ktf_fe

@@ -25,16 +25,20 @@ from .base import Layer
 class FramedSignal:
     """Lazy (batch, frames, width) view over a (batch, samples) signal."""
 
-    def __init__(self, wav, width, shift, ref):
-        self.wav = wav                  # CUDA float32 (B, N)
+    def __init__(self, wav, width, shift, ref, snip_edges=True):
+        self.wav = wav                  # CUDA float32 (B, N), or int16 PCM (B, N)
         self.width = width
         self.shift = shift
+        self.snip_edges = snip_edges    # False: Kaldi's mirror-padded framing, done inside the kernel
         self._ref = ref                 # original user object: decides numpy vs torch outputs
         self._frames = None
 
     @property
     def num_frames(self):
-        return 1 + (self.wav.shape[-1] - self.width) // self.shift
+        n = self.wav.shape[-1]
+        if not self.snip_edges:
+            return (n + self.shift // 2) // self.shift      # kaldi_numpy/frame_extraction.py:78-80
+        return 1 + (n - self.width) // self.shift
 
     @property
     def shape(self):
@@ -42,6 +46,9 @@ class FramedSignal:
 
     def materialize(self):
         if self._frames is None:
+            if not self.snip_edges or self.wav.dtype != torch.float32:
+                raise NotImplementedError("materialised frames need float32 input and snip_edges=True "
+                                          "(the fused MFCC / FilterBank / Windowing layers take both forms)")
             B, n = self.wav.shape
             out = torch.empty(self.shape, device=self.wav.device, dtype=torch.float32)
             N.check(N.lib().ktf_framing_forward(T.ptr(self.wav), B, n, self.wav.stride(0) if B > 1 else n, self.width,
@@ -77,8 +84,12 @@ def _as_framed(inputs):
 class Framing(Layer):
 
     def __init__(self, frame_length_ms=25.0, frame_shift_ms=10.0, sample_frequency=16000.0,
-                 name=None, dynamic_input_shape=False, **kwargs):
+                 name=None, dynamic_input_shape=False, snip_edges=True, **kwargs):
+        """`snip_edges=False` (extension): Kaldi's default framing -- the utterance is mirror-padded inside
+        the kernel, replacing kaldi_numpy.PadWaveform on the host.  int16 inputs (numpy / torch) are taken as raw PCM
+        and converted in the kernel; everything else is float32 in int16 scale like the reference."""
         super().__init__(name=name, trainable=False, **kwargs)
+        self.snipEdges = bool(snip_edges)
         self.sampleFreq = sample_frequency
         self.frameSizeMs = frame_length_ms
         self.frameShiftMs = frame_shift_ms
@@ -123,10 +134,12 @@ class Framing(Layer):
         config.update({"frame_length_ms": self.frameSizeMs, "frame_shift_ms": self.frameShiftMs,
                        "sample_frequency": self.sampleFreq,
                        "dynamic_input_shape": self.dynamicInputShape})
+        if not self.snipEdges:
+            config["snip_edges"] = False
         return config
 
     def call(self, inputs):
-        wav = T.as_device(inputs)
+        wav = T.as_device(inputs, dtype=torch.int16 if T.is_int16(inputs) else torch.float32)
         squeeze = wav.dim() == 1
         if squeeze:
             wav = wav[None]
@@ -139,7 +152,7 @@ class Framing(Layer):
         if not self.dynamicInputShape and self.numInputSamples is not None and n != self.numInputSamples:
             raise ValueError(f"layer was built for {self.numInputSamples} samples, got {n} "
                              "(use dynamic_input_shape=True)")
-        return FramedSignal(wav, self.frameWidth, self.frameShift, inputs)
+        return FramedSignal(wav, self.frameWidth, self.frameShift, inputs, snip_edges=self.snipEdges)
 
 
 # ------------------------------------------------------------------------------------------
@@ -236,29 +249,39 @@ class _Frontend:
         except Exception:
             pass
 
-    def num_frames(self, n):
-        return int(N.lib().ktf_frontend_num_frames(self.handle, n))
+    def num_frames(self, n, snip_edges=True):
+        return int(N.lib().ktf_frontend_num_frames_ex(self.handle, n, int(bool(snip_edges))))
 
-    def forward(self, wav):
-        """wav CUDA (B, n) -> (B, T, out_dim) [, (B, T, 1) energy]."""
+    @staticmethod
+    def _fmt(wav):
+        if wav.dtype == torch.int16:
+            return N.KTF_SAMPLE_S16
+        if wav.dtype != torch.float32:
+            raise ValueError(f"audio must be float32 or int16, got {wav.dtype}")
+        return N.KTF_SAMPLE_F32
+
+    def forward(self, wav, snip_edges=True):
+        """wav CUDA float32 / int16 (B, n) -> (B, T, out_dim) [, (B, T, 1) energy]."""
         B, n = wav.shape
-        Tn = self.num_frames(n)
+        Tn = self.num_frames(n, snip_edges)
         out = torch.empty((B, Tn, self.out_dim), device=wav.device, dtype=torch.float32)
         energy = torch.empty((B, Tn, 1), device=wav.device, dtype=torch.float32) if self.want_energy else None
-        N.check(N.lib().ktf_frontend_forward(self.handle, T.ptr(wav), B, n, wav.stride(0) if B > 1 else n, T.ptr(out),
-                                             T.ptr(energy), T.stream_ptr()))
+        N.check(N.lib().ktf_frontend_forward_ex(self.handle, T.ptr(wav), self._fmt(wav), int(bool(snip_edges)), B, n,
+                                                wav.stride(0) if B > 1 else n, T.ptr(out), T.ptr(energy),
+                                                T.stream_ptr()))
         return out, energy
 
-    def forward_ragged(self, wav_flat, sample_offsets):
+    def forward_ragged(self, wav_flat, sample_offsets, snip_edges=True):
         """wav_flat CUDA (total,), sample_offsets numpy int64 (B+1) -> (total_frames, out_dim), frame offsets."""
         B = len(sample_offsets) - 1
         so = np.ascontiguousarray(sample_offsets, dtype=np.int64)
         fo = np.zeros(B + 1, dtype=np.int64)
         lens = np.diff(so)
-        total = int(sum(self.num_frames(int(l)) for l in lens))
+        total = int(sum(self.num_frames(int(l), snip_edges) for l in lens))
         out = torch.empty((total, self.out_dim), device=wav_flat.device, dtype=torch.float32)
-        N.check(N.lib().ktf_frontend_forward_ragged(self.handle, T.ptr(wav_flat), B, T.host_ptr(so),
-                                                    T.host_ptr(fo), T.ptr(out), None, T.stream_ptr()))
+        N.check(N.lib().ktf_frontend_forward_ragged_ex(self.handle, T.ptr(wav_flat), self._fmt(wav_flat),
+                                                       int(bool(snip_edges)), B, T.host_ptr(so), T.host_ptr(fo),
+                                                       T.ptr(out), None, T.stream_ptr()))
         return out, fo
 
 
@@ -319,7 +342,7 @@ class Windowing(Layer):
         fs, ref = _as_framed(inputs)
         self._maybe_build(fs.shape)
         wav = _dithered(fs.wav, self.dither)
-        out, energy = self._frontend(fs.width, fs.shift).forward(wav)
+        out, energy = self._frontend(fs.width, fs.shift).forward(wav, fs.snip_edges)
         if self.returnEnergy:
             return T.like_input(out, ref), T.like_input(energy, ref)
         return T.like_input(out, ref)
@@ -329,6 +352,7 @@ def _dithered(wav, dither):
     """windowing.py:182-183.  Dither is random by construction: statistically matched only
     (torch Philox on the device), never bit-matched; parity runs use dither=0."""
     if dither != 0.0:
+        wav = wav.to(torch.float32)
         return wav + torch.randn_like(wav) * float(dither)
     return wav
 
@@ -404,7 +428,7 @@ class FilterBank(Layer):
     def call(self, inputs):
         fs, ref = _as_framed(inputs)
         self._maybe_build(fs.shape)
-        out, _ = self._frontend(fs.width, fs.shift).forward(fs.wav)
+        out, _ = self._frontend(fs.width, fs.shift).forward(fs.wav, fs.snip_edges)
         return T.like_input(out, ref)
 
 
@@ -525,7 +549,7 @@ class MFCC(Layer):
         fs, ref = _as_framed(inputs)
         self._maybe_build(fs.shape)
         wav = _dithered(fs.wav, self.windowing.dither)
-        out, _ = self.frontend(fs.width, fs.shift).forward(wav)
+        out, _ = self.frontend(fs.width, fs.shift).forward(wav, fs.snip_edges)
         return T.like_input(out, ref)
 
 

@@ -86,14 +86,16 @@ class XvectorExtractor:
         """Fused framing + MFCC over a ragged batch -> (rows, num_mfccs), frame offsets (CUDA int64)."""
         fe = self.mfcc.frontend(self.framing.frameWidth, self.framing.frameShift)
         if self.mfcc.windowing.dither != 0.0:
+            wav_flat = wav_flat.to(torch.float32)
             wav_flat = wav_flat + torch.randn_like(wav_flat) * float(self.mfcc.windowing.dither)
+        snip = self.framing.snipEdges
         lens = np.diff(sample_offsets)
         if len(lens) > 0 and bool(np.all(lens == lens[0])):
             # uniform batch: no offset tables to upload, nothing on this path synchronises with the host
             B, n = len(lens), int(lens[0])
-            feats, _ = fe.forward(wav_flat.reshape(B, n))
+            feats, _ = fe.forward(wav_flat.reshape(B, n), snip)
             return feats.reshape(-1, feats.shape[-1]), T.uniform_offsets(B, feats.shape[1])
-        feats, fo = fe.forward_ragged(wav_flat, sample_offsets)
+        feats, fo = fe.forward_ragged(wav_flat, sample_offsets, snip)
         return feats, torch.from_numpy(fo).to(wav_flat.device)
 
     def embed(self, feats, offsets, max_frames=None):
@@ -118,12 +120,18 @@ class XvectorExtractor:
                                         T.stream_ptr()))
         return y
 
+    @staticmethod
+    def _audio_dtype(x):
+        """int16 inputs are raw PCM and stay int16 up to the kernel (half the PCIe / HBM bytes)."""
+        return torch.int16 if T.is_int16(x) else torch.float32
+
     def _flatten(self, inputs):
         if isinstance(inputs, (list, tuple)):
-            arrs = [T.as_device(a).reshape(-1) for a in inputs]
+            dt = self._audio_dtype(inputs[0]) if len(inputs) else torch.float32
+            arrs = [T.as_device(a, dtype=dt).reshape(-1) for a in inputs]
             lens = [int(a.numel()) for a in arrs]
             return torch.cat(arrs), np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        x = T.as_device(inputs)
+        x = T.as_device(inputs, dtype=self._audio_dtype(inputs))
         if x.dim() == 1:
             x = x[None]
         if x.dim() != 2:
@@ -134,7 +142,10 @@ class XvectorExtractor:
     def __call__(self, inputs, training: bool = False, return_intermediate: bool = False):
         wav_flat, so = self._flatten(inputs)
         feats, offsets = self.features(wav_flat, so)
-        emb, mask, voffs = self.embed(feats, offsets, max_frames=self.framing.numFrames(int(np.max(np.diff(so)))))
+        n_max = int(np.max(np.diff(so)))
+        max_frames = self.framing.numFrames(n_max) if self.framing.snipEdges else \
+            (n_max + self.framing.frameShift // 2) // self.framing.frameShift
+        emb, mask, voffs = self.embed(feats, offsets, max_frames=max_frames)
         y = self.backend(emb)
         ref = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
         out = T.like_input(y.squeeze(), ref)                      # tf.squeeze (:184)

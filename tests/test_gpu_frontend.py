@@ -122,6 +122,47 @@ def test_mfcc_vs_kaldi_and_oracle(ktf, fe):
     print(f"mfcc: worst rmse vs kaldi {worst_k:.3e}, worst max-abs vs oracle {worst_o:.3e}")
 
 
+def test_mfcc_in_kernel_mirror_padding_and_int16(ktf, fe):
+    # snip-edges=false framing done inside the kernel (index reflection while staging) must equal
+    # the reference's route (kaldi_numpy.PadWaveform on the host, then un-padded framing) on every Kaldi golden
+    # configuration; raw int16 PCM must equal the float32 route bit for bit (the conversion is exact).
+    wav = fe["wav_trimmed"].astype(np.float32)
+    pcm = wav.astype(np.int16)
+    assert np.array_equal(pcm.astype(np.float32), wav)
+    n_mirror = n_pcm = 0
+    for key in fe.files:
+        if not key.startswith("mfcc_conf_"):
+            continue
+        idx = key.split("_")[-1]
+        cfg = helpers.mfcc_conf_to_kwargs(str(fe[key]))
+        host = ktf.layers.MFCC(**cfg["mfcc"])(
+            ktf.layers.Framing(dynamic_input_shape=True, **cfg["framing"])(_padded(wav, cfg)))
+        snip = bool(cfg["snip_edges"])
+        got = ktf.layers.MFCC(**cfg["mfcc"])(
+            ktf.layers.Framing(dynamic_input_shape=True, snip_edges=snip, **cfg["framing"])(wav[None]))
+        assert got.shape == host.shape == fe[f"mfcc_{idx}"].shape, idx
+        assert np.array_equal(got, host), idx
+        assert rmse(fe[f"mfcc_{idx}"], got) < 2.25e-4, idx
+        n_mirror += 0 if snip else 1
+        fr = ktf.layers.Framing(dynamic_input_shape=True, snip_edges=snip, **cfg["framing"])
+        if fr.frameWidth == 400:
+            got16 = ktf.layers.MFCC(**cfg["mfcc"])(fr(pcm[None]))
+            assert np.array_equal(got16, host), idx
+            n_pcm += 1
+        else:
+            with pytest.raises(ValueError):
+                ktf.layers.MFCC(**cfg["mfcc"])(fr(pcm[None]))
+    assert n_mirror >= 20 and n_pcm >= 25, (n_mirror, n_pcm)
+    # batches: ragged edges of every utterance are mirrored independently
+    x = np.stack([wav[:32000], wav[8000:40000], wav[16000:48000]])
+    fr = ktf.layers.Framing(dynamic_input_shape=True, snip_edges=False)
+    m = ktf.layers.MFCC(num_mfccs=30, num_mels=30)
+    batch = m(fr(x))
+    for b in range(3):
+        assert np.array_equal(batch[b], m(fr(x[b:b + 1]))[0])
+        assert np.array_equal(batch[b], m(fr(x[b:b + 1].astype(np.int16)))[0])
+
+
 def test_mfcc_on_materialised_frames(ktf, fe):
     # the MFCC layer also accepts an explicit (B, T, W) frame tensor, like the reference
     wav = fe["wav_trimmed"].astype(np.float32)[None]
@@ -199,6 +240,44 @@ def test_cmvn_batch_and_short(ktf):
         got = ktf.layers.CMVN(window=window, norm_vars=nv)(x)
         want = O.cmvn(x, window=window, norm_vars=nv)
         assert np.max(np.abs(got - want)) < 2e-4, (window, nv)
+
+
+def _cmvn_f64(x, window, norm_vars, padding):
+    x = np.asarray(x, dtype=np.float64)
+    Tn, N = x.shape[1], window
+    if Tn <= N:
+        starts = np.zeros(Tn, dtype=np.int64)
+        N = Tn
+    else:
+        starts = np.clip(np.arange(Tn) - N // 2, 0, Tn - N)
+    cs = np.concatenate([np.zeros_like(x[:, :1]), np.cumsum(x, axis=1)], axis=1)
+    cs2 = np.concatenate([np.zeros_like(x[:, :1]), np.cumsum(x * x, axis=1)], axis=1)
+    mean = (cs[:, starts + N] - cs[:, starts]) / N
+    out = x - mean
+    if norm_vars:
+        out = out / np.sqrt((cs2[:, starts + N] - cs2[:, starts]) / N - mean * mean)
+    if padding == "VALID":
+        out = out[:, window // 2: Tn - (window - 1) // 2]
+    return out
+
+
+@pytest.mark.parametrize("dim", [30, 23, 40])
+def test_cmvn_long_multichunk_vs_oracle(ktf, dim):
+    # utterances spanning several 256-frame CTAs of the staged kernel (halo rows, clamped windows at both ends,
+    # odd feature dims -> unaligned rows), SAME and VALID, with and without variance normalisation
+    rng = np.random.default_rng(dim)
+    x = (rng.standard_normal((3, 1000, dim)) * 5 + rng.standard_normal((3, 1, dim)) * 20).astype(np.float32)
+    for window, nv in [(200, False), (300, True), (257, False), (999, True), (1000, False), (64, True)]:
+        for padding in ("SAME", "VALID"):
+            got = ktf.layers.CMVN(window=window, norm_vars=nv, padding=padding)(x)
+            want = O.cmvn(x, window=window, norm_vars=nv, padding=padding)
+            assert got.shape == want.shape, (window, nv, padding)
+            if want.size:
+                # float64 evaluation of the same windows (cmvn.py:172-237): the float32 oracle carries the rounding
+                # of a 1000-frame float32 cumsum; the kernel has to be at least as close to the truth as it is
+                truth = _cmvn_f64(x, window, nv, padding)
+                assert rmse(truth, got) < max(1e-5, 1.5 * rmse(truth, want)), (window, nv, padding)
+                assert np.max(np.abs(got - truth)) < max(5e-4, 2.0 * np.max(np.abs(want - truth))), (window, nv, padding)
 
 
 def test_vad_vs_kaldi_exact(ktf):
