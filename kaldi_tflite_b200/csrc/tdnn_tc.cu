@@ -578,6 +578,12 @@ __global__ void build_padded_kernel(const long long* __restrict__ offs, long lon
       if (t == 0) f |= kRowFirst;
       if (t == T - 1) f |= kRowLast;
     }
+    // bits 8..11 / 12..15: frames available before / after the (clamped) frame, saturated at 15; bits 16..23: 8 + the
+    // displacement of the clamped frame (halo rows replicate the edge frames) -- used by splice_rows_kernel
+    const long long tc = min(max(t, 0LL), T - 1);
+    f |= (int)min(tc, 15LL) << 8;
+    f |= (int)min(T - 1 - tc, 15LL) << 12;
+    f |= (int)(tc - t + 8) << 16;
     rowmap[p0 + i] = f;
     rowseg[p0 + i] = real ? (int)b : -1 - (int)b;
   }
@@ -621,6 +627,60 @@ __global__ void splice_kernel(const TIn* __restrict__ x, int D, long long x_ld, 
       }
       v[i] = __float2bfloat16_rn(f);
     }
+    *reinterpret_cast<uint4*>(out + p * ld + c0) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// Fast splice for fp32 ragged input with CONSECUTIVE contexts (ctx_k = ctx_0 + k) and an even feature dimension:
+// the K taps of frame t are the contiguous span x[(t + ctx_0) D, (t + ctx_0 + K) D) of the utterance, so an output
+// row is a converted copy of K D consecutive floats.  One thread per 16-byte output chunk; everything it needs to
+// know about its row comes from rowmap / rowseg (two independent loads, no dependent chain through the offsets).
+__global__ void __launch_bounds__(256)
+splice_rows_kernel(const float* __restrict__ x, int D, const int* __restrict__ rowmap, const int* __restrict__ rowseg,
+                   long long prow, int K, int ctx0, __nv_bfloat16* __restrict__ out, long long ld) {
+  const unsigned chunks = (unsigned)(ld >> 3);
+  const int cols = K * D;
+  const unsigned long long total = (unsigned long long)prow * chunks;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (unsigned long long)gridDim.x * blockDim.x) {
+    long long p;
+    if (total < 0xffffffffull) p = (unsigned)idx / chunks; else p = (long long)(idx / chunks);
+    const int c0 = (int)(idx - (unsigned long long)p * chunks) << 3;
+    const int m = rowmap[p], sg = rowseg[p];
+    const int b = sg >= 0 ? sg : -1 - sg;
+    const int lo = (m >> 8) & 15, hi = (m >> 12) & 15, delta = ((m >> 16) & 255) - 8;
+    const long long srow = p - (long long)kHalo * (2 * b + 1) + delta;   // source row of the (clamped) frame
+    const bool inside = (ctx0 >= -lo) && (ctx0 + K - 1 <= hi);
+    float f[8];
+    if (inside) {
+      const float* src = x + (srow + ctx0) * D + c0;
+      if (c0 + 8 <= cols) {
+        const float2* s2 = reinterpret_cast<const float2*>(src);   // D even, c0 % 8 == 0: 8-byte aligned
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 v = s2[i];
+          f[2 * i] = v.x;
+          f[2 * i + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = (c0 + i < cols) ? src[i] : 0.0f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        f[i] = 0.0f;
+        if (c < cols) {
+          const int k = c / D, d = c - k * D;
+          const int o = min(max(ctx0 + k, -lo), hi);
+          f[i] = x[(srow + o) * D + d];
+        }
+      }
+    }
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __float2bfloat16_rn(f[i]);
     *reinterpret_cast<uint4*>(out + p * ld + c0) = *reinterpret_cast<const uint4*>(v);
   }
 }
@@ -882,6 +942,26 @@ void affine_tc_release(ktf_affine* a) {
 
 // Stand-alone layer call (fp32 in / fp32 out): splice to bf16 once, then the tensor-core GEMM.
 // Only SAME padding without subsampling is offered on this engine (the x-vector networks use nothing else).
+
+// Materialises the spliced bf16 operand of a layer fed by fp32 ragged features.
+static int launch_splice_f32(const TcLayer& L, const float* x, const long long* offs, const long long* poffs,
+                      const int* rowmap, const int* rowseg, long long prow, __nv_bfloat16* out, long long ld,
+                      cudaStream_t st) {
+  bool consecutive = (L.D % 2) == 0;
+  for (int k = 1; k < L.K; ++k) consecutive = consecutive && (L.ctx[k] == L.ctx[0] + k);
+  bool small = true;                       // contexts inside the halo (the edge distances saturate at 15)
+  for (int k = 0; k < L.K; ++k) small = small && L.ctx[k] >= -kHalo && L.ctx[k] <= kHalo;
+  if (consecutive && small) {
+    splice_rows_kernel<<<blocks_for(prow * (ld >> 3), 256), 256, 0, st>>>(x, L.D, rowmap, rowseg, prow, L.K, L.ctx[0],
+                                                                           out, ld);
+  } else {
+    splice_kernel<float><<<blocks_for(prow * (ld >> 3), 256), 256, 0, st>>>(x, L.D, L.D, 0, offs, poffs, rowseg, prow,
+                                                                            L.K, L.d_ctx, out, ld);
+  }
+  KTF_LAUNCH_OK();
+  return KTF_OK;
+}
+
 int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in_offsets_dev,
                       const int64_t* out_offsets_dev, int64_t batch, int64_t total_in_rows,
                       int64_t total_out_rows, float* y_dev, float* stats_dev, cudaStream_t st) {
@@ -911,9 +991,8 @@ int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in
 
   build_padded_kernel<<<(unsigned)batch, 128, 0, st>>>((const long long*)in_offsets_dev, batch, poffs, rowmap, rowseg);
   KTF_LAUNCH_OK();
-  splice_kernel<float><<<blocks_for(prow * (ld >> 3), 256), 256, 0, st>>>(
-      x_dev, L.D, L.D, 0, (const long long*)in_offsets_dev, poffs, rowseg, prow, L.K, L.d_ctx, spliced, ld);
-  KTF_LAUNCH_OK();
+  if ((rc = launch_splice_f32(L, x_dev, (const long long*)in_offsets_dev, poffs, rowmap, rowseg, prow, spliced, ld, st)) != KTF_OK)
+    return rc;
   rc = run_layer(L, a, spliced, ld, cols, prow, rowmap, yp, L.U, /*out_bf16=*/false, /*spliced=*/true, st);
   if (rc != KTF_OK) return rc;
   unpad_rows_kernel<<<(unsigned)batch, 256, 0, st>>>(yp, L.U, L.U, (const long long*)in_offsets_dev, poffs, batch, y);
@@ -1094,13 +1173,13 @@ int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int6
       __nv_bfloat16* sp = buf[which];
       const long long ld = round_up(cols, 8);
       const unsigned grid = blocks_for(prow * (ld >> 3), 256);
-      if (i == 0)
-        splice_kernel<float><<<grid, 256, 0, st>>>(feats_dev, L.D, L.D, 0, offs, poffs, rowseg, prow, L.K, L.d_ctx,
-                                                   sp, ld);
-      else
+      if (i == 0) {
+        if ((rc = ktf::launch_splice_f32(L, feats_dev, offs, poffs, rowmap, rowseg, prow, sp, ld, st)) != KTF_OK) return rc;
+      } else {
         splice_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(cur, L.D, cur_ld, 1, offs, poffs, rowseg, prow, L.K,
                                                            L.d_ctx, sp, ld);
-      KTF_LAUNCH_OK();
+        KTF_LAUNCH_OK();
+      }
       A = sp;
       a_ld = ld;
       a_cols = cols;

@@ -107,47 +107,63 @@ __global__ void scan_counts_kernel(const long long* __restrict__ counts, long lo
 }
 
 // One CTA per utterance: stable compaction of kept rows.
+// out[j, :] = feats[index[j], :] for the kept rows (count read from the device: out_offs[batch]).
+__global__ void vad_gather_kernel(const float* __restrict__ feats, int dim, const long long* __restrict__ index,
+                                  const long long* __restrict__ out_offs, long long batch, long long max_rows,
+                                  float* __restrict__ out) {
+  const long long kept = min(out_offs[batch], max_rows);
+  if ((dim & 1) == 0 && kept * (dim >> 1) < 0x7fffffffLL) {
+    // even feature dimension: 8-byte pieces (rows start 8-byte aligned), 32-bit index arithmetic
+    const unsigned half = (unsigned)dim >> 1, total = (unsigned)kept * half;
+    const float2* f2 = reinterpret_cast<const float2*>(feats);
+    float2* o2 = reinterpret_cast<float2*>(out);
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+      const unsigned r = e / half, d = e - r * half;
+      o2[e] = f2[index[r] * half + d];
+    }
+    return;
+  }
+  const long long total = kept * dim;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / dim;
+    const int d = (int)(e - r * dim);
+    out[e] = feats[index[r] * dim + d];
+  }
+}
+
 __global__ void vad_compact_kernel(const float* __restrict__ feats, int dim,
                                    const float* __restrict__ mask,
                                    const long long* __restrict__ offs,
                                    const long long* __restrict__ out_offs,
                                    long long* __restrict__ index, float* __restrict__ out_feats) {
-  __shared__ int s_scan[256];
-  __shared__ int s_base;
+  // one CTA (256 threads) per utterance; chunks of 256 frames: ballot / popc prefix inside a warp, warp totals
+  // through shared memory.  Writes the index list only; the rows are gathered by vad_gather_kernel.
+  __shared__ int s_warp[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long r0 = offs[blockIdx.x];
   const int T = (int)(offs[blockIdx.x + 1] - r0);
   const long long o0 = out_offs[blockIdx.x];
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
-  for (int base = 0; base < T; base += blockDim.x) {
+  int done = 0;                                   // rows kept in earlier chunks (same value in every thread)
+  for (int base = 0; base < T; base += 256) {
     const int t = base + threadIdx.x;
-    const int keep = (t < T && mask[r0 + t] != 0.0f) ? 1 : 0;
-    s_scan[threadIdx.x] = keep;
+    const bool keep = t < T && mask[r0 + t] != 0.0f;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(bal);
     __syncthreads();
-    for (int o = 1; o < blockDim.x; o <<= 1) {
-      const int add = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
-      __syncthreads();
-      s_scan[threadIdx.x] += add;
-      __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int c = s_warp[w];
+      before += (w < warp) ? c : 0;
+      total += c;
     }
-    const int pos = s_base + s_scan[threadIdx.x] - keep;
-    if (keep) index[o0 + pos] = r0 + t;
-    const int chunk_total = s_scan[blockDim.x - 1];
-    if (out_feats != nullptr) {
-      // cooperative row copy: every thread helps copying the rows kept in this chunk
-      __syncthreads();
-      // reuse s_scan as a list of kept local t's
-      const int mypos = s_scan[threadIdx.x] - keep;
-      __syncthreads();
-      if (keep) s_scan[mypos] = t;
-      __syncthreads();
-      for (int e = threadIdx.x; e < chunk_total * dim; e += blockDim.x) {
-        const int rr = e / dim, d = e - rr * dim;
-        out_feats[(o0 + s_base + rr) * dim + d] = feats[(r0 + s_scan[rr]) * dim + d];
-      }
+    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+    if (keep) {
+      index[o0 + done + pos] = r0 + t;
     }
     __syncthreads();
-    if (threadIdx.x == 0) s_base += chunk_total;
+    done += total;
     __syncthreads();
   }
 }
@@ -406,7 +422,6 @@ int ktf_vad_compact(const float* feats_dev, int32_t dim, const float* mask_dev,
   KTF_CHECK_ARG(mask_dev && frame_offsets_dev && out_offsets_dev && index_dev && workspace_dev,
                 "ktf_vad_compact: null argument");
   KTF_CHECK_ARG(out_feats_dev == nullptr || feats_dev != nullptr, "feats_dev required for the gather");
-  (void)total_frames;
   if (batch <= 0) return KTF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   long long* counts = (long long*)workspace_dev;
@@ -419,6 +434,14 @@ int ktf_vad_compact(const float* feats_dev, int32_t dim, const float* mask_dev,
                                                       (const long long*)out_offsets_dev,
                                                       (long long*)index_dev, out_feats_dev);
   KTF_LAUNCH_OK();
+  if (out_feats_dev != nullptr && total_frames > 0) {
+    const long long elems = (long long)total_frames * dim;
+    const long long blocks = std::min<long long>((elems + 255) / 256, (long long)ktf::num_sms() * 32);
+    vad_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(feats_dev, dim, (const long long*)index_dev,
+                                                        (const long long*)out_offsets_dev, batch, total_frames,
+                                                        out_feats_dev);
+    KTF_LAUNCH_OK();
+  }
   return KTF_OK;
 }
 
