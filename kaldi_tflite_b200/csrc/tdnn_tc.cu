@@ -200,9 +200,13 @@ __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
 // sectors).
 // Rows flagged first / last also write their kHalo replicas; rows without kRowStore are skipped.
 // VEC = false (ragged right edge, unaligned output): fp32 staging, bounds-checked scalar stores.
+// VEC staging layout: row r of the 32 x 64-byte block starts at 64 r and its 16-byte piece g sits at position
+// g ^ ((r >> 1) & 3): the eight lanes of a quarter-warp hit 32 different banks both when lanes write their own row
+// (STS.128, rows 8q .. 8q+7) and when four consecutive lanes read back one row (LDS.128, rows 2q', 2q'+1).
+// `plain` (warp-uniform): every one of the warp's 32 rows is a plain kRowStore row -- no per-row flag traffic.
 template <bool OUT_BF16, bool VEC>
 __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float* vb, float relu_lo, float radd,
-                                            unsigned char* stg, int lane, int flags, unsigned char* out0,
+                                            unsigned char* stg, int lane, int flags, bool plain, unsigned char* out0,
                                             long long ld_bytes, int cols_left) {
   const float4* b4 = reinterpret_cast<const float4*>(vb);
   const float4* s4 = reinterpret_cast<const float4*>(vb + BN);
@@ -212,8 +216,10 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
   constexpr int kPieces = kRowSeg / 16;            // 16-byte pieces per row segment
   constexpr int kEs = OUT_BF16 ? 2 : 4;
 #pragma unroll
+  constexpr int kPitch = VEC ? kRowSeg : kStgPitch;
+  const int wsw = (lane >> 1) & 3;                 // swizzle of my own row (VEC)
   for (int pass = 0; pass < 32 / kCols; ++pass) {
-    uint4* mine = reinterpret_cast<uint4*>(stg + lane * kStgPitch);
+    uint4* mine = reinterpret_cast<uint4*>(stg + lane * kPitch);
 #pragma unroll
     for (int g = 0; g < kCols / 8; ++g) {          // 8 columns per group
       const int c8 = pass * (kCols / 8) + g;       // which group of 8 columns of the chunk
@@ -227,13 +233,14 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
         x[4 * h + 3] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo), ss.w, oo.w);
       }
       if (kPacked) {
-        mine[g] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                             pack_bf16x2(x[6], x[7]));
+        mine[g ^ wsw] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                   pack_bf16x2(x[6], x[7]));
       } else {
-        mine[2 * g] = make_uint4(__float_as_uint(x[0] + radd), __float_as_uint(x[1] + radd),
-                                 __float_as_uint(x[2] + radd), __float_as_uint(x[3] + radd));
-        mine[2 * g + 1] = make_uint4(__float_as_uint(x[4] + radd), __float_as_uint(x[5] + radd),
-                                     __float_as_uint(x[6] + radd), __float_as_uint(x[7] + radd));
+        const int sw = VEC ? wsw : 0;
+        mine[(2 * g) ^ sw] = make_uint4(__float_as_uint(x[0] + radd), __float_as_uint(x[1] + radd),
+                                        __float_as_uint(x[2] + radd), __float_as_uint(x[3] + radd));
+        mine[(2 * g + 1) ^ sw] = make_uint4(__float_as_uint(x[4] + radd), __float_as_uint(x[5] + radd),
+                                            __float_as_uint(x[6] + radd), __float_as_uint(x[7] + radd));
       }
     }
     __syncwarp();
@@ -241,9 +248,13 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
 #pragma unroll
       for (int j = 0; j < kPieces; ++j) {
         const int q = j * 32 + lane, rr = q / kPieces, part = q % kPieces;
-        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kStgPitch + part * 16);
-        const int f = __shfl_sync(0xffffffffu, flags, rr);
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kRowSeg + ((part ^ ((rr >> 1) & 3)) * 16));
         unsigned char* dst = out0 + rr * ld_bytes + pass * kRowSeg + part * 16;
+        if (plain) {
+          *reinterpret_cast<uint4*>(dst) = v;
+          continue;
+        }
+        const int f = __shfl_sync(0xffffffffu, flags, rr);
         if (f & kRowStore) {
           *reinterpret_cast<uint4*>(dst) = v;
           if (f & (kRowFirst | kRowLast)) {
@@ -422,6 +433,18 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int colq = (warp - 2) >> 2;         // which kEpiCols of the tile's 256 columns
     const int et = threadIdx.x - 64;          // 0..255
     int staged_nt0 = -1, staged_nt1 = -1;     // n-tile whose epilogue vectors sit in s_vec[0] / s_vec[1]
+    float pre_b = 0.0f, pre_s = 1.0f, pre_o = 0.0f;   // column (nt * BN + et) of bias / scale / offset, prefetched
+    int pre_nt = -1;
+    auto prefetch_vec = [&](int nt_) {
+      if (MODE != kModeStats && et < BN) {
+        const int col = nt_ * BN + et;
+        const bool ok = col < a.n_rows;
+        pre_b = (ok && a.bias) ? a.bias[col] : 0.0f;
+        pre_s = (ok && a.scale) ? a.scale[col] : 1.0f;
+        pre_o = (ok && a.offset) ? a.offset[col] : 0.0f;
+      }
+      pre_nt = nt_;
+    };
     int it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       long long mt;
@@ -494,20 +517,31 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // CTA keeps drawing the same n-tile (always, when gridDim.x is a multiple of n_tiles).
         const int have_nt = acc ? staged_nt1 : staged_nt0;
         if (have_nt != nt) {                                 // uniform over all epilogue threads
+          if (pre_nt != nt) prefetch_vec(nt);                 // normally issued one tile earlier (see below)
           asm volatile("bar.sync 1, 256;\n" ::: "memory");    // every warp is done reading the old vectors
           if (et < BN) {
-            const int col = col_base + et;
-            const bool ok = col < a.n_rows;
-            vb[et] = (ok && a.bias) ? a.bias[col] : 0.0f;
-            vb[BN + et] = (ok && a.scale) ? a.scale[col] : 1.0f;
-            vb[2 * BN + et] = (ok && a.offset) ? a.offset[col] : 0.0f;
+            vb[et] = pre_b;
+            vb[BN + et] = pre_s;
+            vb[2 * BN + et] = pre_o;
           }
           asm volatile("bar.sync 1, 256;\n" ::: "memory");
           if (acc) staged_nt1 = nt; else staged_nt0 = nt;
         }
+        {
+          // the next tile's per-column vectors: global loads issued now, consumed after this tile's stores
+          const long long next = tile + gridDim.x;
+          if (next < total_tiles) {
+            long long mt2;
+            int nt2;
+            tile_coords<MODE>(next, m_tiles, n_tiles, a.reverse, mt2, nt2);
+            const int have2 = acc ? staged_nt0 : staged_nt1;   // the next tile uses the other accumulator stage
+            if (have2 != nt2 && pre_nt != nt2) prefetch_vec(nt2);
+          }
+        }
         int flags = 0;
         if (row < a.m_rows) flags = a.rowmap ? a.rowmap[row] : kRowStore;
         if (a.debug & 1) flags = 0;
+        const bool plain = __all_sync(0xffffffffu, flags == kRowStore);
         float radd = 0.0f;
         if (MODE == kModeF32 && a.row_add != nullptr && row < a.m_rows) radd = a.row_add[row];
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -532,9 +566,9 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (col0 >= n_cols || (a.debug & 2)) continue;  // warp-uniform
           unsigned char* out0 = owarp + (long long)col0 * kEs;
           if (vec_ok && col0 + 32 <= n_cols)
-            store_chunk<kBf16, true>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, out0, ld_bytes, 32);
+            store_chunk<kBf16, true>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, plain, out0, ld_bytes, 32);
           else
-            store_chunk<kBf16, false>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, out0, ld_bytes,
+            store_chunk<kBf16, false>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, false, out0, ld_bytes,
                                       n_cols - col0);
         }
       }
