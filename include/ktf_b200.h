@@ -277,6 +277,12 @@ typedef struct ktf_plda ktf_plda;
 int ktf_plda_create(int32_t dim, const double* mean_host, const double* transform_host,
                     const double* psi_host, int32_t normalize_length, int32_t simple_length_norm,
                     int32_t dtype_bytes, ktf_plda** out);
+/* num_examples: the enrolled vectors scored through this handle are averages over that many
+ * utterances -- plda.py:163-182 (covariance psi + I/n in the length normalisation) and :228-231 (class mean
+ * n psi / (n psi + 1) u, variance 1 + psi / (n psi + 1)).  ktf_plda_create is the n = 1 case. */
+int ktf_plda_create_ex(int32_t dim, const double* mean_host, const double* transform_host,
+                       const double* psi_host, int32_t normalize_length, int32_t simple_length_norm,
+                       int32_t dtype_bytes, double num_examples, ktf_plda** out);
 void ktf_plda_destroy(ktf_plda* p);
 /* x (n, dim) float32 -> u (n, dim) of dtype_bytes each: u = T x - T m, length-normalised
  * (plda.py:184-196). */

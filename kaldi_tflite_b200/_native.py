@@ -81,6 +81,7 @@ _SIGNATURES = {
                                     c_int64, c_int32, c_int32, c_int32, c_float, _P, _P]),
     "ktf_lda_forward": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P, _P]),
     "ktf_plda_create": (c_int32, [c_int32, _P, _P, _P, c_int32, c_int32, c_int32, POINTER(_P)]),
+    "ktf_plda_create_ex": (c_int32, [c_int32, _P, _P, _P, c_int32, c_int32, c_int32, c_double, POINTER(_P)]),
     "ktf_plda_destroy": (None, [_P]),
     "ktf_plda_transform": (c_int32, [_P, _P, c_int64, _P, _P]),
     "ktf_plda_score": (c_int32, [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P]),

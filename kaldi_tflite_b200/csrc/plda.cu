@@ -31,6 +31,7 @@ struct ktf_plda {
   int normalize_length = 1;
   int simple_length_norm = 0;
   int dtype_bytes = 4;
+  double num_examples = 1.0; // utterances averaged into an enrolled vector (plda.py:163-182, 215-231)
   void* d_T = nullptr;       // (dim, dim)
   void* d_offset = nullptr;  // (dim)  -T m
   void* d_psi = nullptr;     // (dim)
@@ -89,7 +90,7 @@ __device__ __forceinline__ T warp_sum(T v) {
 // One warp per vector: length normalisation (plda.py:163-196).
 template <typename T>
 __global__ void plda_norm_kernel(T* __restrict__ u, long long n, int dim, const T* __restrict__ psi,
-                                 int simple) {
+                                 int simple, T inv_examples) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const int lane = threadIdx.x & 31;
@@ -97,7 +98,7 @@ __global__ void plda_norm_kernel(T* __restrict__ u, long long n, int dim, const 
   T acc = T(0);
   for (int d = lane; d < dim; d += 32) {
     const T v = p[d];
-    acc += simple ? v * v : v * v / (psi[d] + T(1));
+    acc += simple ? v * v : v * v / (psi[d] + inv_examples);
   }
   acc = warp_sum(acc);
   const T nf = simple ? sqrt((T)dim) / sqrt(acc) : sqrt((T)dim / acc);
@@ -187,7 +188,7 @@ int transform_impl(const ktf_plda* p, const float* x, int64_t n, T* u, cudaStrea
   KTF_LAUNCH_OK();
   if (p->normalize_length) {
     plda_norm_kernel<T><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(u, n, dim, (const T*)p->d_psi,
-                                                                 p->simple_length_norm);
+                                                                 p->simple_length_norm, (T)(1.0 / p->num_examples));
     KTF_LAUNCH_OK();
   }
   return KTF_OK;
@@ -223,7 +224,15 @@ extern "C" {
 int ktf_plda_create(int32_t dim, const double* mean_host, const double* transform_host,
                     const double* psi_host, int32_t normalize_length, int32_t simple_length_norm,
                     int32_t dtype_bytes, ktf_plda** out) {
+  return ktf_plda_create_ex(dim, mean_host, transform_host, psi_host, normalize_length, simple_length_norm,
+                            dtype_bytes, 1.0, out);
+}
+
+int ktf_plda_create_ex(int32_t dim, const double* mean_host, const double* transform_host,
+                       const double* psi_host, int32_t normalize_length, int32_t simple_length_norm,
+                       int32_t dtype_bytes, double num_examples, ktf_plda** out) {
   KTF_CHECK_ARG(mean_host && transform_host && psi_host && out, "ktf_plda_create: null argument");
+  KTF_CHECK_ARG(num_examples > 0.0, "num_examples must be greater than 0");
   KTF_CHECK_ARG(dim > 0, "dim must be > 0");
   KTF_CHECK_ARG(dtype_bytes == 4 || dtype_bytes == 8, "dtype_bytes must be 4 or 8");
   ktf_plda* p = new ktf_plda();
@@ -231,6 +240,8 @@ int ktf_plda_create(int32_t dim, const double* mean_host, const double* transfor
   p->normalize_length = normalize_length;
   p->simple_length_norm = simple_length_norm;
   p->dtype_bytes = dtype_bytes;
+  p->num_examples = num_examples;
+  const double ne = num_examples;
   const bool f32 = dtype_bytes == 4;
   // Parameters are first rounded to the layer dtype, like tf.constant(..., dtype) (plda.py:103-105).
   auto rnd = [&](double v) { return f32 ? (double)(float)v : v; };
@@ -242,8 +253,8 @@ int ktf_plda_create(int32_t dim, const double* mean_host, const double* transfor
     for (int k = 0; k < dim; ++k) acc += Tm[(size_t)r * dim + k] * rnd(mean_host[k]);
     off[r] = rnd(-acc);                                        // plda.py:116
     psi[r] = rnd(psi_host[r]);
-    const double rr = psi[r] / (psi[r] + 1.0);                 // plda.py:228-231 with n = 1
-    const double v1 = 1.0 + rr, v0 = 1.0 + psi[r];
+    const double rr = ne * psi[r] / (ne * psi[r] + 1.0);       // plda.py:228-231: mean = rr * u_enrolled
+    const double v1 = 1.0 + psi[r] / (ne * psi[r] + 1.0), v0 = 1.0 + psi[r];
     c[r] = rr / v1;
     wa[r] = 0.5 / v0 - 0.5 / v1;
     wb[r] = -0.5 * rr * rr / v1;
@@ -266,7 +277,7 @@ int ktf_plda_create(int32_t dim, const double* mean_host, const double* transfor
   // inside the fp16 range: after length normalisation |u_d| <= sqrt(dim * (psi_d + 1)).
   if (f32 && dim % 8 == 0 && normalize_length && ktf_device_arch() >= 100) {
     double bound = 0.0;
-    for (int r = 0; r < dim; ++r) bound = std::max(bound, sqrt((double)dim * (psi[r] + 1.0)));
+    for (int r = 0; r < dim; ++r) bound = std::max(bound, sqrt((double)dim * (psi[r] + 1.0 / ne)));
     p->use_tc = bound < 3.0e4;
   }
   *out = p;

@@ -41,7 +41,7 @@ class PLDA(Layer):
         self.psi = np.ascontiguousarray(plda_psi, dtype=np.float64)
         self.assertParamShapes()
         self.inputRank = 3
-        self._handle = None
+        self._handles = {}          # one ktf_plda handle per num_examples value
 
     def assertParamShapes(self):
         assert self.mean.ndim == 1, f"plda_mean must be a vector, got dimension={self.mean.ndim}"
@@ -72,22 +72,29 @@ class PLDA(Layer):
                        "return_transformed": self.returnTransformed})
         return config
 
-    @property
-    def handle(self):
-        if self._handle is None:
+    def handle_for(self, num_examples=1.0):
+        """The constants of the score depend on how many utterances an enrolled vector averages
+        (plda.py:163-182, 215-231), so handles are cached per `num_examples`."""
+        key = float(num_examples)
+        assert key > 0, "num_examples must be greater than 1"          # plda.py:164
+        if key not in self._handles:
             N.require_cuda()
             h = ctypes.c_void_p()
-            N.check(N.lib().ktf_plda_create(self.dim, T.host_ptr(self.mean), T.host_ptr(self.transformMat),
-                                            T.host_ptr(self.psi), int(self.normalizeLength),
-                                            int(self.simpleLengthNorm),
-                                            8 if self.paramDtype == np.float64 else 4, ctypes.byref(h)))
-            self._handle = h
-        return self._handle
+            N.check(N.lib().ktf_plda_create_ex(self.dim, T.host_ptr(self.mean), T.host_ptr(self.transformMat),
+                                               T.host_ptr(self.psi), int(self.normalizeLength),
+                                               int(self.simpleLengthNorm),
+                                               8 if self.paramDtype == np.float64 else 4, key, ctypes.byref(h)))
+            self._handles[key] = h
+        return self._handles[key]
+
+    @property
+    def handle(self):
+        return self.handle_for(1.0)
 
     def __del__(self):
         try:
-            if self._handle:
-                N.lib().ktf_plda_destroy(self._handle)
+            for h in self._handles.values():
+                N.lib().ktf_plda_destroy(h)
         except Exception:
             pass
 
@@ -95,21 +102,22 @@ class PLDA(Layer):
     def torchDtype(self):
         return torch.float64 if self.paramDtype == np.float64 else torch.float32
 
-    def transformVector(self, x2d):
+    def transformVector(self, x2d, num_examples=1.0):
         """(n, dim) float32 CUDA -> (n, dim) in the layer dtype: plda.py:184-196."""
         n = x2d.shape[0]
         u = torch.empty((n, self.dim), device=x2d.device, dtype=self.torchDtype)
-        N.check(N.lib().ktf_plda_transform(self.handle, T.ptr(x2d), n, T.ptr(u), T.stream_ptr()))
+        N.check(N.lib().ktf_plda_transform(self.handle_for(num_examples), T.ptr(x2d), n, T.ptr(u), T.stream_ptr()))
         return u
 
-    def logLikelihoodRatio(self, u_test, u_enroll=None, out=None):
-        """scores[i, j] = LLR(test i | enrolled j): plda.py:215-245 (all-pairs)."""
+    def logLikelihoodRatio(self, u_test, u_enroll=None, out=None, num_examples=1.0):
+        """scores[i, j] = LLR(test i | enrolled j): plda.py:215-245 (all-pairs); `num_examples` = utterances averaged
+        into each enrolled vector."""
         u_enroll = u_test if u_enroll is None else u_enroll
         nt, ne = u_test.shape[0], u_enroll.shape[0]
         if out is None:
             out = torch.empty((nt, ne), device=u_test.device, dtype=self.torchDtype)
-        N.check(N.lib().ktf_plda_score(self.handle, T.ptr(u_test), nt, T.ptr(u_enroll), ne, T.ptr(out),
-                                       out.stride(0), T.stream_ptr()))
+        N.check(N.lib().ktf_plda_score(self.handle_for(num_examples), T.ptr(u_test), nt, T.ptr(u_enroll), ne,
+                                       T.ptr(out), out.stride(0), T.stream_ptr()))
         return out
 
     def call(self, inputs):

@@ -139,6 +139,30 @@ def synthetic_plda(dim, seed=1234):
     return mean, Tm, psi
 
 
+def test_plda_num_examples_vs_oracle(ktf):
+    # enrolled vectors that average n utterances (plda.py:163-182, 215-231), both dtypes and
+    # both length normalisations, against the float64 oracle of the direct broadcast form
+    import torch
+    dim, n = 128, 300
+    mean, Tm, psi = synthetic_plda(dim)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    for ne in (1.0, 3.0, 10.0):
+        for simple in (False, True):
+            u64 = O.plda_transform(x, mean, Tm, psi, True, simple, np.float64, num_examples=ne)
+            want = O.plda_llr(u64, psi, np.float64, num_examples=ne)
+            for dt in (np.float32, np.float64):
+                layer = ktf.layers.PLDA(dim, mean, Tm, psi, simple_length_norm=simple, dtype=dt)
+                u = layer.transformVector(xd, num_examples=ne)
+                got = layer.logLikelihoodRatio(u, num_examples=ne).cpu().numpy()
+                assert np.max(np.abs(u.cpu().numpy() - u64)) < (1e-4 if dt == np.float32 else 1e-9), (ne, simple, dt)
+                tol = 1e-3 if dt == np.float32 else 1e-9
+                assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)) < tol, (ne, simple, dt)
+    with pytest.raises(AssertionError):
+        ktf.layers.PLDA(dim, mean, Tm, psi).transformVector(xd, num_examples=0)
+
+
 def test_plda_random_vs_oracle(ktf):
     # SURVEY.md 8d cfg5 parity: |delta| <= 1e-3 * max(|s|, 1) against the float64 oracle
     dim, n = 128, 700
