@@ -176,7 +176,7 @@ struct ktf_frontend {
   float* d_lifter = nullptr;
   // 16 x 16 fast path (frontend_r16.cu); null when the configuration is not eligible
   float* d_r16 = nullptr;
-  int r16_blob_floats = 0, r16_nf = 0, r16_melw_floats = 0;
+  int r16_blob_floats = 0, r16_nf = 0, r16_melw_floats = 0, r16_dct_sym = 0;
 };
 
 namespace ktf_fe {

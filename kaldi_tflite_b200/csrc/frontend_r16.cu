@@ -29,6 +29,9 @@
 
 using namespace ktf_fe;
 
+// the per-mode tails of the item loop end in `continue`; the code after them is dead for that instantiation only
+#pragma nv_diag_suppress 128
+
 namespace {
 
 constexpr int kW = 400;               // frame width of the fast path
@@ -47,10 +50,46 @@ constexpr int kOffTw2 = kOffTw1 + 8 * kTw1Stride;
 constexpr int kOffUnits = kOffTw2 + 8 * kTw2Stride;  // [8 lanes][SD] unit descriptors, then [8 lanes][SW] unit weights
 __host__ __device__ constexpr int pad4mod32(int x) { return x + (((4 - x) % 32) + 32) % 32; }
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Packed FP32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): one issue slot per complex add / half a complex multiply.  The
+// operand modifiers of the SASS forms (half swap, per-half negation, scalar broadcast) absorb the shuffles that a
+// complex product needs, so the packing costs no extra moves.
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7};"
+      " fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return sub2(a, b); }
+// (a.x b.x - a.y b.y, a.y b.x + a.x b.y)
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+  return fma2(a, make_float2(b.x, b.x), mul2(make_float2(a.y, a.x), make_float2(-b.y, b.y)));
+}
+// a + (-i) b = (a.x + b.y, a.y - b.x)  and  a - (-i) b
+__device__ __forceinline__ float2 add_mi(float2 a, float2 b) {
+  return fma2(make_float2(b.y, b.x), make_float2(1.0f, -1.0f), a);
+}
+__device__ __forceinline__ float2 sub_mi(float2 a, float2 b) {
+  return fma2(make_float2(b.y, b.x), make_float2(-1.0f, 1.0f), a);
 }
 
 // x * W_16^M with compile-time M (W_16 = exp(-2 pi i / 16)).
@@ -58,12 +97,12 @@ template <int M>
 __device__ __forceinline__ float2 mul_w16(float2 x) {
   constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
   if constexpr (M == 0) return x;
-  else if constexpr (M == 1) return make_float2(fmaf(x.x, c1, x.y * s1), fmaf(x.y, c1, -x.x * s1));
-  else if constexpr (M == 2) return make_float2((x.x + x.y) * h, (x.y - x.x) * h);
-  else if constexpr (M == 3) return make_float2(fmaf(x.x, s1, x.y * c1), fmaf(x.y, s1, -x.x * c1));
+  else if constexpr (M == 1) return cmul(x, make_float2(c1, -s1));
+  else if constexpr (M == 2) return cmul(x, make_float2(h, -h));
+  else if constexpr (M == 3) return cmul(x, make_float2(s1, -c1));
   else if constexpr (M == 4) return make_float2(x.y, -x.x);
-  else if constexpr (M == 6) return make_float2((x.y - x.x) * h, -(x.x + x.y) * h);
-  else if constexpr (M == 9) return make_float2(fmaf(-x.x, c1, -x.y * s1), fmaf(-x.y, c1, x.x * s1));
+  else if constexpr (M == 6) return cmul(x, make_float2(-h, -h));
+  else if constexpr (M == 9) return cmul(x, make_float2(-c1, s1));
   else return x;
 }
 
@@ -72,8 +111,8 @@ __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d)
   const float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = csub(b, d);
   a = cadd(s0, s2);
   c = csub(s0, s2);
-  b = make_float2(s1.x + s3.y, s1.y - s3.x);
-  d = make_float2(s1.x - s3.y, s1.y + s3.x);
+  b = add_mi(s1, s3);
+  d = sub_mi(s1, s3);
 }
 
 // dft4 with d == 0 on input (x + 0 is not folded by the compiler: -0 + 0 = +0 under IEEE rules).
@@ -81,8 +120,8 @@ __device__ __forceinline__ void dft4_d0(float2& a, float2& b, float2& c, float2&
   const float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = b;
   a = cadd(s0, s2);
   c = csub(s0, s2);
-  b = make_float2(s1.x + s2.y, s1.y - s2.x);
-  d = make_float2(s1.x - s2.y, s1.y + s2.x);
+  b = add_mi(s1, s2);
+  d = sub_mi(s1, s2);
 }
 
 // 16-point complex FFT in registers (radix 4 x 4, decimation in frequency).  Input natural order,
@@ -113,11 +152,14 @@ __device__ __forceinline__ void fft16(float2 (&x)[16]) {
   dft4(x[12], x[13], x[14], x[15]);
 }
 
-// DCT_REG (MFCC with <= 32 mel bins): lane c keeps column c of the DCT matrix in registers and produces cepstrum
+// DCT_REG 1 / 2 (MFCC with <= 32 mel bins): lane c keeps column c of the DCT matrix in registers and produces cepstrum
 // c of all 4 frames, so the DCT reads no table at all (only broadcast loads of the log-mel rows).
 // PCM16: the input is int16 PCM; the span buffer holds the raw 16-bit samples (half the HBM / L2 / smem bytes) and
 // they are converted when the window is applied.
-template <int OUTPUT, bool RAW_ENERGY, bool DCT_REG, bool PCM16>
+// DCT_REG == 2: the matrix has the DCT-II mirror symmetry D[M-1-i][c] = (-1)^c D[i][c] (checked on the host), so
+// even cepstra are dot products with s[i] = lm[i] + lm[M-1-i] and odd ones with d[i] = lm[i] - lm[M-1-i]: half the
+// coefficient registers, half the broadcast loads and half the FMAs.
+template <int OUTPUT, bool RAW_ENERGY, int DCT_REG, bool PCM16>
 __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const FrontendArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int NU = a.r16_nf;                        // mel units (8 bins each) per lane
@@ -182,10 +224,12 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
   float* lm_row = (OUTPUT == KTF_OUT_MFCC) ? s_LM + f * LMS : s_out + f * M;
   const float pc = a.preemph > 0.0f ? a.preemph : 0.0f;
   const int prev_lane = (lane & 24) | ((j + 7) & 7);   // the lane that owns the 4 samples before mine
-  float dreg[DCT_REG ? 32 : 1];
+  constexpr int kDregs = DCT_REG == 2 ? 16 : (DCT_REG == 1 ? 32 : 1);
+  float dreg[kDregs];
   if (DCT_REG) {
+    const int rows = DCT_REG == 2 ? (M + 1) / 2 : M;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) dreg[i] = (i < M && lane < a.Kc) ? s_dct[i * 32 + lane] : 0.0f;
+    for (int i = 0; i < kDregs; ++i) dreg[i] = (i < rows && lane < a.Kc) ? s_dct[i * 32 + lane] : 0.0f;
   }
 
   for (; item < a.total_groups; item += warp_stride) {
@@ -198,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
     {
       float4 xv[kRows];
       float xm[kRows];
-      float sum = 0.0f;
+      float2 sum2 = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         if (PCM16) {
@@ -212,26 +256,31 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
         // sample 32r + 4j - 1 is the last of the previous lane's four (lane 0: lane 7's four of the previous row)
         const float give = (r > 0 && j == 7) ? xv[r - 1].w : xv[r].w;
         xm[r] = __shfl_sync(0xffffffffu, give, prev_lane);
-        sum += (xv[r].x + xv[r].y) + (xv[r].z + xv[r].w);
+        sum2 = add2(sum2, add2(make_float2(xv[r].x, xv[r].y), make_float2(xv[r].z, xv[r].w)));
       }
       float mean = 0.0f;
-      if (a.remove_dc) mean = group_sum8(sum) / (float)kW;
+      if (a.remove_dc) mean = group_sum8(sum2.x + sum2.y) / (float)kW;
+      const float2 mean2 = make_float2(mean, mean);
+      float2 e2 = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         const float4 w = *reinterpret_cast<const float4*>(wn + 32 * r);
-        float d0 = xv[r].x - mean, d1 = xv[r].y - mean, d2 = xv[r].z - mean, d3 = xv[r].w - mean;
+        float2 d01 = sub2(make_float2(xv[r].x, xv[r].y), mean2);
+        float2 d23 = sub2(make_float2(xv[r].z, xv[r].w), mean2);
         float dm = xm[r] - mean;
-        if (r == 0) dm = j0 ? d0 : dm;
-        if (r == kRows - 1 && !tail_ok) { d0 = 0.f; d1 = 0.f; d2 = 0.f; d3 = 0.f; dm = 0.f; }
-        if (RAW_ENERGY) esum = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, esum))));
-        const float y0 = (d0 - pc * dm) * w.x;
-        const float y1 = (d1 - pc * d0) * w.y;
-        const float y2 = (d2 - pc * d1) * w.z;
-        const float y3 = (d3 - pc * d2) * w.w;
-        if (!RAW_ENERGY) esum = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, esum))));
-        ze[r] = make_float2(y0, y1);
-        zo[r] = make_float2(y2, y3);
+        if (r == 0) dm = j0 ? d01.x : dm;
+        if (r == kRows - 1 && !tail_ok) { d01 = make_float2(0.f, 0.f); d23 = make_float2(0.f, 0.f); dm = 0.f; }
+        if (RAW_ENERGY) { e2 = fma2(d01, d01, e2); e2 = fma2(d23, d23, e2); }
+        // pre-emphasis pairs (d[i-1], d[i]) straddle the packed pairs, so that step stays scalar
+        const float2 t01 = make_float2(fmaf(-pc, dm, d01.x), fmaf(-pc, d01.x, d01.y));
+        const float2 t23 = make_float2(fmaf(-pc, d01.y, d23.x), fmaf(-pc, d23.x, d23.y));
+        const float2 y01 = mul2(t01, make_float2(w.x, w.y));
+        const float2 y23 = mul2(t23, make_float2(w.z, w.w));
+        if (!RAW_ENERGY) { e2 = fma2(y01, y01, e2); e2 = fma2(y23, y23, e2); }
+        ze[r] = y01;
+        zo[r] = y23;
       }
+      esum = e2.x + e2.y;
 #pragma unroll
       for (int r = kRows; r < 16; ++r) { ze[r] = make_float2(0.f, 0.f); zo[r] = make_float2(0.f, 0.f); }
     }
@@ -309,9 +358,9 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
       }
       const float4 t4 = t2[e >> 1];
       const float2 t = (e & 1) ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
-      const float2 S = make_float2(zk.x + zp.x, zk.y - zp.y);
-      const float2 D = make_float2(zk.x - zp.x, zk.y + zp.y);
-      const float2 G = cmul(t, D);
+      const float2 S = fma2(zp, make_float2(1.0f, -1.0f), zk);    // zk + conj(zp)
+      const float2 D = fma2(zp, make_float2(-1.0f, 1.0f), zk);    // zk - conj(zp)
+      const float2 G = cmul(D, t);
       const float2 u = cadd(S, G), v = csub(S, G);
       const float p1 = fmaf(u.x, u.x, u.y * u.y);
       float p2 = fmaf(v.x, v.x, v.y * v.y);
@@ -342,19 +391,68 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
       const int slot = d.x >> 16;
       const float keep_next = __int_as_float(d.y);
       d = udesc[u + 1];   // one padding descriptor follows the last unit
-      float acc0 = w0.x * q0.x, acc1 = w1.x * q1.x;
-      acc0 = fmaf(w0.y, q0.y, acc0);
-      acc1 = fmaf(w1.y, q1.y, acc1);
-      acc0 = fmaf(w0.z, q0.z, acc0);
-      acc1 = fmaf(w1.z, q1.z, acc1);
-      acc0 = fmaf(w0.w, q0.w, acc0);
-      acc1 = fmaf(w1.w, q1.w, acc1);
+      float2 acc0 = mul2(make_float2(w0.x, w0.y), make_float2(q0.x, q0.y));
+      float2 acc1 = mul2(make_float2(w1.x, w1.y), make_float2(q1.x, q1.y));
+      acc0 = fma2(make_float2(w0.z, w0.w), make_float2(q0.z, q0.w), acc0);
+      acc1 = fma2(make_float2(w1.z, w1.w), make_float2(q1.z, q1.w), acc1);
+      acc0 = add2(acc0, acc1);
       // the only serial dependency between units: keep = 1 inside a filter, 0 after its last unit
-      run = fmaf(run, keep, acc0 + acc1);
+      run = fmaf(run, keep, acc0.x + acc0.y);
       keep = keep_next;
       lm_acc[slot] = run;   // partial sums are overwritten by the filter's last unit (same lane, program order)
     }
     __syncwarp();
+    if (OUTPUT == KTF_OUT_MFCC && DCT_REG == 2) {
+      // log (filterbank.py:240) of the mirrored pairs (i, M-1-i), i = 2j, 2j+1; their sum and difference go to the
+      // (now dead) power tile of the frame: [0, 16) = s, [16, 32) = d
+      const int i0 = 2 * j, half = (M + 1) >> 1;
+      float2 lo = *reinterpret_cast<const float2*>(lm_acc + i0);
+      const int m0 = M - 1 - i0, m1 = M - 2 - i0;
+      float2 hi = make_float2(lm_acc[m0 < 0 ? 0 : m0], lm_acc[m1 < 0 ? 0 : m1]);
+      if (a.use_log) {
+        lo.x = __logf(fmaxf(lo.x, 0.0f) + a.eps);
+        lo.y = __logf(fmaxf(lo.y, 0.0f) + a.eps);
+        hi.x = __logf(fmaxf(hi.x, 0.0f) + a.eps);
+        hi.y = __logf(fmaxf(hi.y, 0.0f) + a.eps);
+      }
+      float2 sv = add2(lo, hi), dv = sub2(lo, hi);
+      if (i0 == m0) { sv.x = lo.x; dv.x = 0.0f; }               // the self-paired middle bin of an odd M
+      if (i0 + 1 == m1) { sv.y = lo.y; dv.y = 0.0f; }
+      if (i0 >= half) { sv.x = 0.0f; dv.x = 0.0f; }
+      if (i0 + 1 >= half) { sv.y = 0.0f; dv.y = 0.0f; }
+      *reinterpret_cast<float2*>(tile + i0) = sv;
+      *reinterpret_cast<float2*>(tile + 16 + i0) = dv;
+      __syncwarp();
+      float2 o2[4];   // even-i and odd-i partial sums
+#pragma unroll
+      for (int ff = 0; ff < 4; ++ff) o2[ff] = make_float2(0.0f, 0.0f);
+      const float* vrow = s_T + 16 * (lane & 1);
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+#pragma unroll
+        for (int ff = 0; ff < 4; ++ff) {
+          const float4 v = *reinterpret_cast<const float4*>(vrow + ff * kTile + 4 * i4);
+          o2[ff] = fma2(make_float2(v.x, v.y), make_float2(dreg[4 * i4], dreg[4 * i4 + 1]), o2[ff]);
+          o2[ff] = fma2(make_float2(v.z, v.w), make_float2(dreg[4 * i4 + 2], dreg[4 * i4 + 3]), o2[ff]);
+        }
+      }
+      // C0 <- log-energy (mfcc.py:219-228): frame ff's value lives in lanes 8 ff .. 8 ff + 7
+      float o[4];
+#pragma unroll
+      for (int ff = 0; ff < 4; ++ff) {
+        o[ff] = o2[ff].x + o2[ff].y;
+        const float le = __shfl_sync(0xffffffffu, log_e, 8 * ff);
+        if (lane == 0 && a.use_energy) o[ff] = le;
+      }
+      if (lane < a.Kc) {
+        float* dst = a.out + (me.out_row0 + me.frame0) * (long long)a.Kc + lane;
+#pragma unroll
+        for (int ff = 0; ff < 4; ++ff)
+          if (ff < me.nvalid) dst[ff * a.Kc] = o[ff];
+      }
+      continue;
+    }
+
     // log (filterbank.py:240); each lane finishes mel bins 4j .. 4j+3 (+32, +64, ...) of its frame
     for (int i0 = 4 * j; i0 < M; i0 += 32) {
       float4 v = *reinterpret_cast<const float4*>(lm_acc + i0);
@@ -377,22 +475,25 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
     }
     __syncwarp();
 
-    if (OUTPUT == KTF_OUT_MFCC && DCT_REG) {
+    if (OUTPUT == KTF_OUT_MFCC && DCT_REG == 1) {
       // ---- DCT (dct.py:176) with the lifter (mfcc.py:212) folded into the matrix: lane c = cepstrum c of all 4 frames
-      float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      float2 o2[4];   // even-i and odd-i partial sums
+#pragma unroll
+      for (int ff = 0; ff < 4; ++ff) o2[ff] = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int i4 = 0; i4 < 8; ++i4) {
         if (4 * i4 < M) {
 #pragma unroll
           for (int ff = 0; ff < 4; ++ff) {
             const float4 lm = *reinterpret_cast<const float4*>(s_LM + ff * LMS + 4 * i4);   // broadcast
-            o[ff] = fmaf(lm.x, dreg[4 * i4], o[ff]);
-            o[ff] = fmaf(lm.y, dreg[4 * i4 + 1], o[ff]);
-            o[ff] = fmaf(lm.z, dreg[4 * i4 + 2], o[ff]);
-            o[ff] = fmaf(lm.w, dreg[4 * i4 + 3], o[ff]);
+            o2[ff] = fma2(make_float2(lm.x, lm.y), make_float2(dreg[4 * i4], dreg[4 * i4 + 1]), o2[ff]);
+            o2[ff] = fma2(make_float2(lm.z, lm.w), make_float2(dreg[4 * i4 + 2], dreg[4 * i4 + 3]), o2[ff]);
           }
         }
       }
+      float o[4];
+#pragma unroll
+      for (int ff = 0; ff < 4; ++ff) o[ff] = o2[ff].x + o2[ff].y;
       // C0 <- log-energy (mfcc.py:219-228): frame ff's value lives in lanes 8 ff .. 8 ff + 7
 #pragma unroll
       for (int ff = 0; ff < 4; ++ff) {
@@ -469,7 +570,7 @@ size_t r16_smem_bytes(const ktf_frontend* fe) {
   return ((size_t)fe->r16_blob_floats + kWarpsPerCta * warp_floats) * sizeof(float);
 }
 
-template <int OUTPUT, bool RAW, bool DCT_REG, bool PCM16>
+template <int OUTPUT, bool RAW, int DCT_REG, bool PCM16>
 int launch_r16(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
   const size_t smem = r16_smem_bytes(fe);
   auto kern = frontend_r16_kernel<OUTPUT, RAW, DCT_REG, PCM16>;
@@ -616,6 +717,7 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
       blob[kOffTw2 + j * kTw2Stride + e * 2] = (float)(-sin(th));
       blob[kOffTw2 + j * kTw2Stride + e * 2 + 1] = (float)(-cos(th));
     }
+  fe->r16_dct_sym = 0;
   if (c.output == KTF_OUT_MFCC) {
     float* dp = blob.data() + kOffUnits + 8 * SD + 8 * SW;
     for (int i = 0; i < M; ++i)
@@ -623,6 +725,17 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
         const float lf = (c.apply_lifter && lifter_host) ? lifter_host[cc] : 1.0f;
         dp[(size_t)i * 32 + cc] = dct_host[(size_t)i * Kc + cc] * lf;
       }
+    // DCT-II mirror symmetry (dct.py:98-143 builds cos(pi/M (i + 1/2) c), so row M-1-i is (-1)^c times row i; the
+    // two are rounded from float64 separately, hence the 1-ulp tolerance): enables the half-size register DCT
+    float dmax = 0.0f;
+    for (int i = 0; i < M * Kc; ++i) dmax = std::max(dmax, fabsf(dct_host[i]));
+    bool sym = M <= 32;
+    for (int i = 0; i < M && sym; ++i)
+      for (int cc = 0; cc < Kc && sym; ++cc) {
+        const float sgn = (cc & 1) ? -1.0f : 1.0f;
+        sym = fabsf(dct_host[(size_t)(M - 1 - i) * Kc + cc] - sgn * dct_host[(size_t)i * Kc + cc]) <= 2.5e-7f * dmax;
+      }
+    fe->r16_dct_sym = sym ? 1 : 0;
   }
 
   fe->r16_blob_floats = blob_floats;
@@ -632,7 +745,7 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
   return ktf::upload(&fe->d_r16, blob.data(), blob.size());
 }
 
-template <int OUTPUT, bool DCT_REG>
+template <int OUTPUT, int DCT_REG>
 int launch_r16_sel(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
   const bool raw = fe->cfg.raw_energy != 0, pcm = a.wav16 != nullptr;
   if (raw) return pcm ? launch_r16<OUTPUT, true, DCT_REG, true>(fe, a, st) : launch_r16<OUTPUT, true, DCT_REG, false>(fe, a, st);
@@ -641,10 +754,13 @@ int launch_r16_sel(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
 
 int r16_launch(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
   if (fe->cfg.output == KTF_OUT_MFCC) {
-    if (fe->cfg.num_mels <= 32) return launch_r16_sel<KTF_OUT_MFCC, true>(fe, a, st);
-    return launch_r16_sel<KTF_OUT_MFCC, false>(fe, a, st);
+    if (fe->cfg.num_mels <= 32) {
+      if (fe->r16_dct_sym) return launch_r16_sel<KTF_OUT_MFCC, 2>(fe, a, st);
+      return launch_r16_sel<KTF_OUT_MFCC, 1>(fe, a, st);
+    }
+    return launch_r16_sel<KTF_OUT_MFCC, 0>(fe, a, st);
   }
-  return launch_r16_sel<KTF_OUT_FBANK, false>(fe, a, st);
+  return launch_r16_sel<KTF_OUT_FBANK, 0>(fe, a, st);
 }
 
 }  // namespace ktf_fe
