@@ -218,8 +218,14 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
   float* qa_hi = tile + (j0 ? 8 : j);            // e >= 8
   float* qb_lo = tile + 16 - j;                  // e < 8  (lane 0: 256 - 16 e)
   float* qb_hi = tile + (j0 ? 8 : 16 - j);       // e >= 8
-  const int2* udesc = reinterpret_cast<const int2*>(s_udesc + j * SD);
-  const float4* uwts = reinterpret_cast<const float4*>(s_uwts + j * SW);
+  // mel phase: a quarter-warp (the conflict domain of LDS.128) holds schedule rows 2q, 2q+1 of all 4 frames.  The
+  // frame tiles are 2 bank groups apart and rows of opposite parity only ever read chunks of opposite parity (host
+  // schedule), so the 8 lanes always hit 8 different bank groups.
+  const int mf = (lane >> 1) & 3, mj = (lane & 1) | ((lane >> 3) << 1);
+  const int2* udesc = reinterpret_cast<const int2*>(s_udesc + mj * SD);
+  const float4* uwts = reinterpret_cast<const float4*>(s_uwts + mj * SW);
+  const float* mel_tile = s_T + mf * kTile;
+  float* mel_acc = s_LM + mf * LMS;
   float* lm_acc = s_LM + f * LMS;
   float* lm_row = (OUTPUT == KTF_OUT_MFCC) ? s_LM + f * LMS : s_out + f * M;
   const float pc = a.preemph > 0.0f ? a.preemph : 0.0f;
@@ -377,13 +383,13 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
     }
     __syncwarp();
 
-    // ---- mel bank (filterbank.py:238-240): lane j walks its NU units of 8 bins; the units of a filter are
-    //      consecutive on one lane, the running sum is flushed at the filter's last unit.
+    // ---- mel bank (filterbank.py:238-240): lane (mf, mj) walks the NU units (8 bins each) of schedule row mj on frame
+    //      mf; the units of a filter are consecutive on one row, the running sum is flushed at the filter's last unit.
     float run = 0.0f, keep = 0.0f;
     int2 d = udesc[0];   // (first bin | filter slot << 16, keep)
 #pragma unroll 2
     for (int u = 0; u < NU; ++u) {
-      const float* q = tile + (d.x & 0xffff);
+      const float* q = mel_tile + (d.x & 0xffff);
       const float4 q0 = *reinterpret_cast<const float4*>(q);
       const float4 q1 = *reinterpret_cast<const float4*>(q + 4);
       const float4 w0 = uwts[2 * u];
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
       // the only serial dependency between units: keep = 1 inside a filter, 0 after its last unit
       run = fmaf(run, keep, acc0.x + acc0.y);
       keep = keep_next;
-      lm_acc[slot] = run;   // partial sums are overwritten by the filter's last unit (same lane, program order)
+      mel_acc[slot] = run;   // partial sums are overwritten by the filter's last unit (same lane, program order)
     }
     __syncwarp();
     if (OUTPUT == KTF_OUT_MFCC && DCT_REG == 2) {
@@ -615,63 +621,29 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
     if (lo >= 0) { c0 = lo >> 2; n = (hi >> 2) - c0 + 1; }
     filt[i] = {c0, n};
   }
+  // Rows of even index take filters whose first chunk is even, odd rows odd ones (units advance by two chunks, so the
+  // parity holds for every unit of the filter): together with the kernel's lane mapping this makes every LDS.128 of
+  // the mel phase bank-conflict free.  A filter with an odd number of chunks may start one (all-zero) chunk early at
+  // no cost in units, which lets it go to either parity; filters go longest-first to the least loaded allowed row.
   std::vector<int> order((size_t)M);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return filt[x].n > filt[y].n; });
   std::vector<std::vector<int>> lanes(8);
   int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int i : order) {
-    int best = 0;
-    for (int l = 1; l < 8; ++l)
-      if (load[l] < load[best]) best = l;
+    if (filt[i].n == 0) { filt[i].c0 = 0; }
+    const bool flexible = (filt[i].n & 1) && filt[i].c0 > 0;
+    int best = -1;
+    for (int l = 0; l < 8; ++l) {
+      if (!flexible && filt[i].n > 0 && (l & 1) != (filt[i].c0 & 1)) continue;
+      if (best < 0 || load[l] < load[best]) best = l;
+    }
+    if (filt[i].n > 0 && (best & 1) != (filt[i].c0 & 1)) { filt[i].c0 -= 1; filt[i].n += 1; }
     lanes[best].push_back(i);
     load[best] += (filt[i].n + 1) / 2;
   }
   int NU = 1;
   for (int l = 0; l < 8; ++l) NU = std::max(NU, load[l]);
-
-  // Order of the filters inside each lane: at step u the 8 lanes of a frame read 8 different 4-bin chunks with one
-  // LDS.128; two chunks collide when they differ but are equal mod 8 (same banks).  A pairwise-swap local search
-  // minimises the number of extra wavefronts over the whole schedule; padding units read a free bank group.
-  auto unit_chunks = [&](int l, std::vector<int>& out) {
-    out.clear();
-    for (int i : lanes[l])
-      for (int cc = 0; cc < filt[i].n; cc += 2) out.push_back(filt[i].c0 + cc);
-  };
-  auto schedule_cost = [&]() {
-    std::vector<int> uc[8];
-    for (int l = 0; l < 8; ++l) unit_chunks(l, uc[l]);
-    int cost = 0;
-    for (int u = 0; u < NU; ++u) {
-      int worst = 1;
-      for (int g = 0; g < 8; ++g) {
-        int distinct[8], nd = 0;
-        for (int l = 0; l < 8; ++l) {
-          if (u >= (int)uc[l].size() || (uc[l][u] & 7) != g) continue;
-          bool seen = false;
-          for (int t = 0; t < nd; ++t) seen = seen || distinct[t] == uc[l][u];
-          if (!seen) distinct[nd++] = uc[l][u];
-        }
-        worst = std::max(worst, nd);
-      }
-      cost += worst - 1;
-    }
-    return cost;
-  };
-  {
-    int best = schedule_cost();
-    bool improved = best > 0;
-    for (int round = 0; round < 16 && improved; ++round) {
-      improved = false;
-      for (int l = 0; l < 8 && best > 0; ++l)
-        for (size_t x = 0; x < lanes[l].size(); ++x)
-          for (size_t y = x + 1; y < lanes[l].size(); ++y) {
-            std::swap(lanes[l][x], lanes[l][y]);
-            const int cst = schedule_cost();
-            if (cst < best) { best = cst; improved = true; } else std::swap(lanes[l][x], lanes[l][y]);
-          }
-    }
-  }
 
   const int SD = pad4mod32(2 * (NU + 1)), SW = pad4mod32(8 * NU);
   const int LMS = r16_lms(c);
@@ -696,7 +668,7 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
           uw[8 * u + b8] = in ? mel_bank_host[(size_t)k * M + i] * 0.25f : 0.0f;   // the kernel stores 4|X|^2
         }
       }
-    // padding: zero weights, spare slot, chunk l (lane-distinct banks)
+    // padding: zero weights, spare slot, chunk l (the row's own parity)
     for (; u <= NU; ++u) { ud[2 * u] = (4 * l) | ((LMS - 1) << 16); ud[2 * u + 1] = 0; }
   }
 
