@@ -43,8 +43,8 @@ constexpr int kTile = 584;            // floats per frame tile (16 * 36 = 576, +
 constexpr int kOffWin = 0;
 // per-lane table rows are padded to a stride of 4 (mod 32) floats: the 8 lanes of a frame (one LDS.128
 // quarter-warp) then read 8 different bank groups
-constexpr int kTw1Stride = 68;                  // floats per lane: [16 k1][4] + 4
-constexpr int kTw2Stride = 36;                  // floats per lane: [16 e][2] + 4
+constexpr int kTw1Stride = 36;                  // floats per lane: [16 k1][2] + 4   (W_256^(2j k1))
+constexpr int kTw2Stride = 4;                   // floats per lane: untangling base twiddles for e < 8 and e >= 8
 constexpr int kOffTw1 = kOffWin + kWinPad;
 constexpr int kOffTw2 = kOffTw1 + 8 * kTw1Stride;
 constexpr int kOffUnits = kOffTw2 + 8 * kTw2Stride;  // [8 lanes][SD] unit descriptors, then [8 lanes][SW] unit weights
@@ -78,6 +78,12 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
       : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
   return r;
 }
+// cos / sin of 2 pi k / 256 and 2 pi e / 32 for k, e < 16 (folded to immediates by the unrolled loops)
+__device__ constexpr float kCos256[16] = {1.0f, 0.99969881869620425f, 0.99879545620517241f, 0.99729045667869021f, 0.99518472667219693f, 0.99247953459870997f, 0.98917650996478101f, 0.98527764238894122f, 0.98078528040323043f, 0.97570213003852857f, 0.97003125319454397f, 0.96377606579543984f, 0.95694033573220882f, 0.94952818059303667f, 0.94154406518302081f, 0.93299279883473896f};
+__device__ constexpr float kSin256[16] = {0.0f, 0.024541228522912288f, 0.049067674327418015f, 0.073564563599667426f, 0.098017140329560604f, 0.1224106751992162f, 0.14673047445536175f, 0.17096188876030122f, 0.19509032201612825f, 0.2191012401568698f, 0.24298017990326387f, 0.26671275747489837f, 0.29028467725446233f, 0.31368174039889152f, 0.33688985339222005f, 0.35989503653498811f};
+__device__ constexpr float kCos32[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f, 0.0f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f};
+__device__ constexpr float kSin32[16] = {0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f, 0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f, 1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f, 0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f};
+
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return sub2(a, b); }
 // (a.x b.x - a.y b.y, a.y b.x + a.x b.y)
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
   const int SD = pad4mod32(2 * (NU + 1)), SW = pad4mod32(8 * NU);
   const int M = a.M;
   float* s_win = smem + kOffWin;
-  const float4* s_tw1 = reinterpret_cast<const float4*>(smem + kOffTw1);
+  const float2* s_tw1 = reinterpret_cast<const float2*>(smem + kOffTw1);
   const float4* s_tw2 = reinterpret_cast<const float4*>(smem + kOffTw2);
   const float* s_udesc = smem + kOffUnits;
   const float* s_uwts = s_udesc + 8 * SD;
@@ -206,8 +212,8 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
   const float* fr = s_span + f * a.shift + 4 * j;
   const short* fr16 = reinterpret_cast<const short*>(s_span) + f * a.shift + 4 * j;
   const float* wn = s_win + 4 * j;
-  const float4* tw1 = s_tw1 + j * (kTw1Stride / 4);
-  const float4* tw2 = s_tw2 + j * (kTw2Stride / 4);
+  const float2* tw1 = s_tw1 + j * (kTw1Stride / 2);
+  const float4 tw2 = s_tw2[j];   // (base for e < 8, base for e >= 8): W_512^j, lane 0: 1 and W_512^8
   float* tile = s_T + f * kTile;
   float* tile_w = tile + 4 * j;
   const int col_a = j, col_b = j0 ? 8 : 16 - j;
@@ -310,7 +316,9 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
     }
 
     // ---- stage 1: two 16-point FFTs over n1, twiddle W_256^(n2 k1), rows [k1][n2] of the tile ---------
-    float4 t1[16];   // issued ahead of the FFTs so that their latency is covered by arithmetic
+    // Twiddles: the table holds W_256^(2j k1) for the even column n2 = 2j; the odd column's W_256^((2j+1) k1) is that
+    // times the compile-time constant W_256^k1 (two packed instructions instead of 8 more bytes of LDS per k1).
+    float2 t1[16];   // issued ahead of the FFTs so that their latency is covered by arithmetic
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) t1[k1] = tw1[k1];
     fft16<true>(ze);
@@ -321,9 +329,10 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
     for (int k1 = 0; k1 < 16; ++k1) {
       float2 e = ze[pos16(k1)], o = zo[pos16(k1)];
       if (k1 > 0) {
-        const float4 t = t1[k1];
-        e = cmul(e, make_float2(t.x, t.y));
-        o = cmul(o, make_float2(t.z, t.w));
+        const float2 te = t1[k1];
+        const float2 to = cmul(te, make_float2(kCos256[k1], -kSin256[k1]));
+        e = cmul(e, te);
+        o = cmul(o, to);
       }
       *reinterpret_cast<float4*>(tile_w + k1 * kRowStride) = make_float4(e.x, e.y, o.x, o.y);
     }
@@ -340,9 +349,6 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
       vb[2 * c] = make_float2(rb.x, rb.y);
       vb[2 * c + 1] = make_float2(rb.z, rb.w);
     }
-    float4 t2[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) t2[e] = tw2[e];
     __syncwarp();  // the tile is consumed; it is reused as the power buffer below
     fft16<false>(va);
     fft16<false>(vb);
@@ -362,8 +368,9 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
         zk = make_float2(j0 ? k_self.x : k_reg.x, j0 ? k_self.y : k_reg.y);
         zp = vb[pos16(15 - e)];
       }
-      const float4 t4 = t2[e >> 1];
-      const float2 t = (e & 1) ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
+      // t = -i W_512^k, k = j + 16 e (lane 0: 16 e, then 8 + 16 e): the lane's base twiddle times the constant -i W_32^e
+      const float2 t = cmul(e < 8 ? make_float2(tw2.x, tw2.y) : make_float2(tw2.z, tw2.w),
+                            make_float2(-kSin32[e], -kCos32[e]));
       const float2 S = fma2(zp, make_float2(1.0f, -1.0f), zk);    // zk + conj(zp)
       const float2 D = fma2(zp, make_float2(-1.0f, 1.0f), zk);    // zk - conj(zp)
       const float2 G = cmul(D, t);
@@ -674,21 +681,18 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
 
   const double PI = 3.14159265358979323846;
   for (int j = 0; j < 8; ++j)
-    for (int k1 = 0; k1 < 16; ++k1)
-      for (int h = 0; h < 2; ++h) {
-        const int n2 = 2 * j + h;
-        const double th = -2.0 * PI * (double)((n2 * k1) % 256) / 256.0;
-        blob[kOffTw1 + j * kTw1Stride + k1 * 4 + 2 * h] = (float)cos(th);
-        blob[kOffTw1 + j * kTw1Stride + k1 * 4 + 2 * h + 1] = (float)sin(th);
-      }
-  for (int j = 0; j < 8; ++j)
-    for (int e = 0; e < 16; ++e) {
-      int k = j + 16 * e;
-      if (j == 0) k = e < 8 ? 16 * e : 8 + 16 * e;
-      const double th = 2.0 * PI * (double)k / 512.0;   // -i * exp(-i th) = (-sin th, -cos th)
-      blob[kOffTw2 + j * kTw2Stride + e * 2] = (float)(-sin(th));
-      blob[kOffTw2 + j * kTw2Stride + e * 2 + 1] = (float)(-cos(th));
+    for (int k1 = 0; k1 < 16; ++k1) {
+      const double th = -2.0 * PI * (double)((2 * j * k1) % 256) / 256.0;
+      blob[kOffTw1 + j * kTw1Stride + k1 * 2] = (float)cos(th);
+      blob[kOffTw1 + j * kTw1Stride + k1 * 2 + 1] = (float)sin(th);
     }
+  for (int j = 0; j < 8; ++j) {   // W_512^k of the lane's first column for e < 8 and e >= 8
+    const int k_lo = j, k_hi = (j == 0) ? 8 : j;
+    blob[kOffTw2 + j * kTw2Stride + 0] = (float)cos(2.0 * PI * k_lo / 512.0);
+    blob[kOffTw2 + j * kTw2Stride + 1] = (float)(-sin(2.0 * PI * k_lo / 512.0));
+    blob[kOffTw2 + j * kTw2Stride + 2] = (float)cos(2.0 * PI * k_hi / 512.0);
+    blob[kOffTw2 + j * kTw2Stride + 3] = (float)(-sin(2.0 * PI * k_hi / 512.0));
+  }
   fe->r16_dct_sym = 0;
   if (c.output == KTF_OUT_MFCC) {
     float* dp = blob.data() + kOffUnits + 8 * SD + 8 * SW;
