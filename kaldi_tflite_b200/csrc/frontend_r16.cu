@@ -35,6 +35,11 @@ using namespace ktf_fe;
 namespace {
 
 constexpr int kW = 400;               // frame width of the fast path
+// 4 warps per CTA, 3 CTAs per SM (168 registers): registers are allocated in units of 4 warps, so the next step up
+// would be 16 resident warps at 128 registers, which spills the two 16-point FFTs (measured: 14 warps as 2 x 7 end
+// up as ONE resident CTA)
+constexpr int kR16Warps = 4;
+constexpr int kR16Threads = kR16Warps * 32;
 constexpr int kRows = 13;             // ceil(400 / 32) rows of 32 samples
 constexpr int kTailLanes = 4;         // lanes j < 4 own valid samples in row 12 (400 = 12 * 32 + 16)
 constexpr int kWinPad = 416;          // window table padded with zeros to 13 * 32
@@ -166,7 +171,7 @@ __device__ __forceinline__ void fft16(float2 (&x)[16]) {
 // even cepstra are dot products with s[i] = lm[i] + lm[M-1-i] and odd ones with d[i] = lm[i] - lm[M-1-i]: half the
 // coefficient registers, half the broadcast loads and half the FMAs.
 template <int OUTPUT, bool RAW_ENERGY, int DCT_REG, bool PCM16>
-__global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const FrontendArgs a) {
+__global__ void __launch_bounds__(kR16Threads, 3) frontend_r16_kernel(const FrontendArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int NU = a.r16_nf;                        // mel units (8 bins each) per lane
   const int SD = pad4mod32(2 * (NU + 1)), SW = pad4mod32(8 * NU);
@@ -190,8 +195,8 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
   float* s_LM = s_T + 4 * kTile;             // mel sums, then log-mel [f][LMS]
   float* s_out = s_LM + 4 * LMS;
 
-  const long long warp_global = (long long)blockIdx.x * kWarpsPerCta + warp;
-  const long long warp_stride = (long long)gridDim.x * kWarpsPerCta;
+  const long long warp_global = (long long)blockIdx.x * kR16Warps + warp;
+  const long long warp_stride = (long long)gridDim.x * kR16Warps;
 
   Item cur;
   long long item = warp_global;
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
     cur = decode_item(a, item);
     if (PCM16) stage_span16(a, cur, reinterpret_cast<short*>(s_span), lane); else stage_span(a, cur, s_span, lane);
   }
-  for (int i = threadIdx.x; i < a.r16_blob_floats; i += kThreads) smem[i] = a.r16_blob[i];
+  for (int i = threadIdx.x; i < a.r16_blob_floats; i += kR16Threads) smem[i] = a.r16_blob[i];
   for (int i = lane; i < 4 * LMS; i += 32) s_LM[i] = 0.0f;   // slots >= M stay finite
   __syncthreads();
 
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
   // frame tiles are 2 bank groups apart and rows of opposite parity only ever read chunks of opposite parity (host
   // schedule), so the 8 lanes always hit 8 different bank groups.
   const int mf = (lane >> 1) & 3, mj = (lane & 1) | ((lane >> 3) << 1);
-  const int2* udesc = reinterpret_cast<const int2*>(s_udesc + mj * SD);
+  const int4* udesc4 = reinterpret_cast<const int4*>(s_udesc + mj * SD);
   const float4* uwts = reinterpret_cast<const float4*>(s_uwts + mj * SW);
   const float* mel_tile = s_T + mf * kTile;
   float* mel_acc = s_LM + mf * LMS;
@@ -392,27 +397,34 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_r16_kernel(const Fronten
 
     // ---- mel bank (filterbank.py:238-240): lane (mf, mj) walks the NU units (8 bins each) of schedule row mj on frame
     //      mf; the units of a filter are consecutive on one row, the running sum is flushed at the filter's last unit.
+    //      Four units per trip (the host pads every row to a multiple of four with zero-weight units): all 18 loads of
+    //      a trip are in flight before the first product, instead of a descriptor -> address -> data chain per unit.
     float run = 0.0f, keep = 0.0f;
-    int2 d = udesc[0];   // (first bin | filter slot << 16, keep)
-#pragma unroll 2
-    for (int u = 0; u < NU; ++u) {
-      const float* q = mel_tile + (d.x & 0xffff);
-      const float4 q0 = *reinterpret_cast<const float4*>(q);
-      const float4 q1 = *reinterpret_cast<const float4*>(q + 4);
-      const float4 w0 = uwts[2 * u];
-      const float4 w1 = uwts[2 * u + 1];
-      const int slot = d.x >> 16;
-      const float keep_next = __int_as_float(d.y);
-      d = udesc[u + 1];   // one padding descriptor follows the last unit
-      float2 acc0 = mul2(make_float2(w0.x, w0.y), make_float2(q0.x, q0.y));
-      float2 acc1 = mul2(make_float2(w1.x, w1.y), make_float2(q1.x, q1.y));
-      acc0 = fma2(make_float2(w0.z, w0.w), make_float2(q0.z, q0.w), acc0);
-      acc1 = fma2(make_float2(w1.z, w1.w), make_float2(q1.z, q1.w), acc1);
-      acc0 = add2(acc0, acc1);
-      // the only serial dependency between units: keep = 1 inside a filter, 0 after its last unit
-      run = fmaf(run, keep, acc0.x + acc0.y);
-      keep = keep_next;
-      mel_acc[slot] = run;   // partial sums are overwritten by the filter's last unit (same lane, program order)
+    for (int u = 0; u < NU; u += 4) {
+      const int4 da = udesc4[u >> 1], db = udesc4[(u >> 1) + 1];   // (first bin | filter slot << 16, keep) x 4
+      const int dx[4] = {da.x, da.z, db.x, db.z};
+      const float kp[4] = {__int_as_float(da.y), __int_as_float(da.w), __int_as_float(db.y), __int_as_float(db.w)};
+      float4 q0[4], q1[4], w0[4], w1[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float* q = mel_tile + (dx[t] & 0xffff);
+        q0[t] = *reinterpret_cast<const float4*>(q);
+        q1[t] = *reinterpret_cast<const float4*>(q + 4);
+        w0[t] = uwts[2 * (u + t)];
+        w1[t] = uwts[2 * (u + t) + 1];
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 acc0 = mul2(make_float2(w0[t].x, w0[t].y), make_float2(q0[t].x, q0[t].y));
+        float2 acc1 = mul2(make_float2(w1[t].x, w1[t].y), make_float2(q1[t].x, q1[t].y));
+        acc0 = fma2(make_float2(w0[t].z, w0[t].w), make_float2(q0[t].z, q0[t].w), acc0);
+        acc1 = fma2(make_float2(w1[t].z, w1[t].w), make_float2(q1[t].z, q1[t].w), acc1);
+        acc0 = add2(acc0, acc1);
+        // the only serial dependency between units: keep = 1 inside a filter, 0 after its last unit
+        run = fmaf(run, keep, acc0.x + acc0.y);
+        keep = kp[t];
+        mel_acc[dx[t] >> 16] = run;   // partial sums are overwritten by the filter's last unit (same lane, program order)
+      }
     }
     __syncwarp();
     if (OUTPUT == KTF_OUT_MFCC && DCT_REG == 2) {
@@ -580,7 +592,7 @@ size_t r16_smem_bytes(const ktf_frontend* fe) {
   const int out_row = fe->out_dim;
   const int out_sz = (4 * out_row + 3) & ~3;
   const size_t warp_floats = (size_t)span_p + 4 * kTile + 4 * LMS + out_sz;
-  return ((size_t)fe->r16_blob_floats + kWarpsPerCta * warp_floats) * sizeof(float);
+  return ((size_t)fe->r16_blob_floats + kR16Warps * warp_floats) * sizeof(float);
 }
 
 template <int OUTPUT, bool RAW, int DCT_REG, bool PCM16>
@@ -590,12 +602,12 @@ int launch_r16(const ktf_frontend* fe, FrontendArgs& a, cudaStream_t st) {
   KTF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)std::max<size_t>(smem, 48 * 1024)));
   int occ = 0;
-  KTF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+  KTF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kR16Threads, smem));
   if (occ < 1) occ = 1;
-  const long long ctas_needed = (a.total_groups + kWarpsPerCta - 1) / kWarpsPerCta;
+  const long long ctas_needed = (a.total_groups + kR16Warps - 1) / kR16Warps;
   const long long grid = std::min<long long>(ctas_needed, (long long)ktf::num_sms() * occ);
   if (grid <= 0) return KTF_OK;
-  kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
+  kern<<<(unsigned)grid, kR16Threads, smem, st>>>(a);
   KTF_LAUNCH_OK();
   return KTF_OK;
 }
@@ -651,6 +663,7 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
   }
   int NU = 1;
   for (int l = 0; l < 8; ++l) NU = std::max(NU, load[l]);
+  NU = (NU + 3) & ~3;   // the kernel walks four units per trip
 
   const int SD = pad4mod32(2 * (NU + 1)), SW = pad4mod32(8 * NU);
   const int LMS = r16_lms(c);
