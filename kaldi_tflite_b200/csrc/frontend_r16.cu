@@ -174,7 +174,7 @@ template <int OUTPUT, bool RAW_ENERGY, int DCT_REG, bool PCM16>
 __global__ void __launch_bounds__(kR16Threads, 3) frontend_r16_kernel(const FrontendArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int NU = a.r16_nf;                        // mel units (8 bins each) per lane
-  const int SD = pad4mod32(2 * (NU + 1)), SW = pad4mod32(8 * NU);
+  const int SD = pad4mod32(2 * ((NU + 3) & ~3)), SW = pad4mod32(8 * NU);
   const int M = a.M;
   float* s_win = smem + kOffWin;
   const float2* s_tw1 = reinterpret_cast<const float2*>(smem + kOffTw1);
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kR16Threads, 3) frontend_r16_kernel(const Fron
   const int LMS = DCT_REG ? 36 : ((M + 3) & ~3) + 4;   // log-mel row stride (one spare slot for padding units)
   const int out_row = (OUTPUT == KTF_OUT_MFCC) ? a.Kc : M;
   const int out_sz = (4 * out_row + 3) & ~3;
-  const int warp_floats = span_p + 4 * kTile + 4 * LMS + out_sz;
+  const int warp_floats = (span_p + 4 * kTile + 4 * LMS + out_sz + 31) & ~31;   // 128-byte aligned per-warp regions
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s_span = s_warp0 + warp * warp_floats;
   float* s_T = s_span + span_p;
@@ -591,7 +591,7 @@ size_t r16_smem_bytes(const ktf_frontend* fe) {
   const int LMS = r16_lms(fe->cfg);
   const int out_row = fe->out_dim;
   const int out_sz = (4 * out_row + 3) & ~3;
-  const size_t warp_floats = (size_t)span_p + 4 * kTile + 4 * LMS + out_sz;
+  const size_t warp_floats = ((size_t)span_p + 4 * kTile + 4 * LMS + out_sz + 31) & ~(size_t)31;
   return ((size_t)fe->r16_blob_floats + kR16Warps * warp_floats) * sizeof(float);
 }
 
@@ -663,15 +663,16 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
   }
   int NU = 1;
   for (int l = 0; l < 8; ++l) NU = std::max(NU, load[l]);
-  NU = (NU + 3) & ~3;   // the kernel walks four units per trip
+  NU = (NU + 3) & ~3;   // the kernel walks four units per trip (a partial last trip costs more than the padding)
 
-  const int SD = pad4mod32(2 * (NU + 1)), SW = pad4mod32(8 * NU);
+  // descriptors are read four at a time (the last trip may be partial: pad them to a multiple of four)
+  const int SD = pad4mod32(2 * ((NU + 3) & ~3)), SW = pad4mod32(8 * NU);
   const int LMS = r16_lms(c);
   const float one = 1.0f;
   int one_bits;
   memcpy(&one_bits, &one, sizeof(one_bits));
   const int dct_floats = c.output == KTF_OUT_MFCC ? M * 32 : 0;
-  const int blob_floats = kOffUnits + 8 * SD + 8 * SW + dct_floats;
+  const int blob_floats = (kOffUnits + 8 * SD + 8 * SW + dct_floats + 31) & ~31;
   std::vector<float> blob((size_t)blob_floats, 0.0f);
   for (int i = 0; i < kW; ++i) blob[kOffWin + i] = window_host[i];
   for (int l = 0; l < 8; ++l) {
@@ -689,7 +690,7 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
         }
       }
     // padding: zero weights, spare slot, chunk l (the row's own parity)
-    for (; u <= NU; ++u) { ud[2 * u] = (4 * l) | ((LMS - 1) << 16); ud[2 * u + 1] = 0; }
+    for (; u < ((NU + 3) & ~3); ++u) { ud[2 * u] = (4 * l) | ((LMS - 1) << 16); ud[2 * u + 1] = 0; }
   }
 
   const double PI = 3.14159265358979323846;
