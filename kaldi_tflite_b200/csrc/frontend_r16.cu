@@ -38,6 +38,9 @@ constexpr int kW = 400;               // frame width of the fast path
 // 4 warps per CTA, 3 CTAs per SM (168 registers): registers are allocated in units of 4 warps, so the next step up
 // would be 16 resident warps at 128 registers, which spills the two 16-point FFTs (measured: 14 warps as 2 x 7 end
 // up as ONE resident CTA)
+#ifndef KTF_R16_MINB
+#define KTF_R16_MINB 3
+#endif
 constexpr int kR16Warps = 4;
 constexpr int kR16Threads = kR16Warps * 32;
 constexpr int kRows = 13;             // ceil(400 / 32) rows of 32 samples
@@ -48,8 +51,25 @@ constexpr int kTile = 584;            // floats per frame tile (16 * 36 = 576, +
 constexpr int kOffWin = 0;
 // per-lane table rows are padded to a stride of 4 (mod 32) floats: the 8 lanes of a frame (one LDS.128
 // quarter-warp) then read 8 different bank groups
+// Twiddles: read from exactly rounded per-lane tables (0), or derived in the kernel from a smaller table and
+// compile-time constants (1: fewer LDS bytes and registers, but two more roundings per twiddle, which shows on mel
+// bins 60 dB below the frame peak).
+#ifndef KTF_R16_TW1_DERIVED
+#define KTF_R16_TW1_DERIVED 0
+#endif
+#ifndef KTF_R16_TW2_DERIVED
+#define KTF_R16_TW2_DERIVED 0
+#endif
+#if KTF_R16_TW1_DERIVED
 constexpr int kTw1Stride = 36;                  // floats per lane: [16 k1][2] + 4   (W_256^(2j k1))
+#else
+constexpr int kTw1Stride = 68;                  // floats per lane: [16 k1][4] + 4   (W_256^(2j k1), W_256^((2j+1) k1))
+#endif
+#if KTF_R16_TW2_DERIVED
 constexpr int kTw2Stride = 4;                   // floats per lane: untangling base twiddles for e < 8 and e >= 8
+#else
+constexpr int kTw2Stride = 36;                  // floats per lane: [16 e][2] + 4
+#endif
 constexpr int kOffTw1 = kOffWin + kWinPad;
 constexpr int kOffTw2 = kOffTw1 + 8 * kTw1Stride;
 constexpr int kOffUnits = kOffTw2 + 8 * kTw2Stride;  // [8 lanes][SD] unit descriptors, then [8 lanes][SW] unit weights
@@ -171,13 +191,17 @@ __device__ __forceinline__ void fft16(float2 (&x)[16]) {
 // even cepstra are dot products with s[i] = lm[i] + lm[M-1-i] and odd ones with d[i] = lm[i] - lm[M-1-i]: half the
 // coefficient registers, half the broadcast loads and half the FMAs.
 template <int OUTPUT, bool RAW_ENERGY, int DCT_REG, bool PCM16>
-__global__ void __launch_bounds__(kR16Threads, 3) frontend_r16_kernel(const FrontendArgs a) {
+__global__ void __launch_bounds__(kR16Threads, KTF_R16_MINB) frontend_r16_kernel(const FrontendArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int NU = a.r16_nf;                        // mel units (8 bins each) per lane
   const int SD = pad4mod32(2 * ((NU + 3) & ~3)), SW = pad4mod32(8 * NU);
   const int M = a.M;
   float* s_win = smem + kOffWin;
+#if KTF_R16_TW1_DERIVED
   const float2* s_tw1 = reinterpret_cast<const float2*>(smem + kOffTw1);
+#else
+  const float4* s_tw1 = reinterpret_cast<const float4*>(smem + kOffTw1);
+#endif
   const float4* s_tw2 = reinterpret_cast<const float4*>(smem + kOffTw2);
   const float* s_udesc = smem + kOffUnits;
   const float* s_uwts = s_udesc + 8 * SD;
@@ -217,8 +241,16 @@ __global__ void __launch_bounds__(kR16Threads, 3) frontend_r16_kernel(const Fron
   const float* fr = s_span + f * a.shift + 4 * j;
   const short* fr16 = reinterpret_cast<const short*>(s_span) + f * a.shift + 4 * j;
   const float* wn = s_win + 4 * j;
+#if KTF_R16_TW1_DERIVED
   const float2* tw1 = s_tw1 + j * (kTw1Stride / 2);
+#else
+  const float4* tw1 = s_tw1 + j * (kTw1Stride / 4);
+#endif
+#if KTF_R16_TW2_DERIVED
   const float4 tw2 = s_tw2[j];   // (base for e < 8, base for e >= 8): W_512^j, lane 0: 1 and W_512^8
+#else
+  const float4* tw2 = s_tw2 + j * (kTw2Stride / 4);
+#endif
   float* tile = s_T + f * kTile;
   float* tile_w = tile + 4 * j;
   const int col_a = j, col_b = j0 ? 8 : 16 - j;
@@ -263,9 +295,16 @@ __global__ void __launch_bounds__(kR16Threads, 3) frontend_r16_kernel(const Fron
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         if (PCM16) {
+          // int16 -> float without I2F (quarter-rate pipe): x ^ 0x8000 = x + 32768 as an unsigned 16-bit value u,
+          // placed in the mantissa of 2^23 it reads 8388608 + u, and subtracting 8421376 is exact
           const uint2 raw = *reinterpret_cast<const uint2*>(fr16 + 32 * r);
-          xv[r] = make_float4((float)(short)(raw.x & 0xffffu), (float)(short)(raw.x >> 16),
-                              (float)(short)(raw.y & 0xffffu), (float)(short)(raw.y >> 16));
+          const unsigned ua = raw.x ^ 0x80008000u, ub = raw.y ^ 0x80008000u;
+          const float2 bias2 = make_float2(8421376.0f, 8421376.0f);
+          const float2 lo = sub2(make_float2(__uint_as_float(__byte_perm(ua, 0x4B000000u, 0x7610)),
+                                             __uint_as_float(__byte_perm(ua, 0x4B000000u, 0x7632))), bias2);
+          const float2 hi = sub2(make_float2(__uint_as_float(__byte_perm(ub, 0x4B000000u, 0x7610)),
+                                             __uint_as_float(__byte_perm(ub, 0x4B000000u, 0x7632))), bias2);
+          xv[r] = make_float4(lo.x, lo.y, hi.x, hi.y);
         } else {
           xv[r] = *reinterpret_cast<const float4*>(fr + 32 * r);
         }
@@ -321,9 +360,13 @@ __global__ void __launch_bounds__(kR16Threads, 3) frontend_r16_kernel(const Fron
     }
 
     // ---- stage 1: two 16-point FFTs over n1, twiddle W_256^(n2 k1), rows [k1][n2] of the tile ---------
+#if KTF_R16_TW1_DERIVED
     // Twiddles: the table holds W_256^(2j k1) for the even column n2 = 2j; the odd column's W_256^((2j+1) k1) is that
     // times the compile-time constant W_256^k1 (two packed instructions instead of 8 more bytes of LDS per k1).
     float2 t1[16];   // issued ahead of the FFTs so that their latency is covered by arithmetic
+#else
+    float4 t1[16];   // issued ahead of the FFTs so that their latency is covered by arithmetic
+#endif
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) t1[k1] = tw1[k1];
     fft16<true>(ze);
@@ -334,8 +377,12 @@ __global__ void __launch_bounds__(kR16Threads, 3) frontend_r16_kernel(const Fron
     for (int k1 = 0; k1 < 16; ++k1) {
       float2 e = ze[pos16(k1)], o = zo[pos16(k1)];
       if (k1 > 0) {
+#if KTF_R16_TW1_DERIVED
         const float2 te = t1[k1];
         const float2 to = cmul(te, make_float2(kCos256[k1], -kSin256[k1]));
+#else
+        const float2 te = make_float2(t1[k1].x, t1[k1].y), to = make_float2(t1[k1].z, t1[k1].w);
+#endif
         e = cmul(e, te);
         o = cmul(o, to);
       }
@@ -354,6 +401,11 @@ __global__ void __launch_bounds__(kR16Threads, 3) frontend_r16_kernel(const Fron
       vb[2 * c] = make_float2(rb.x, rb.y);
       vb[2 * c + 1] = make_float2(rb.z, rb.w);
     }
+#if !KTF_R16_TW2_DERIVED
+    float4 t2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t2[e] = tw2[e];
+#endif
     __syncwarp();  // the tile is consumed; it is reused as the power buffer below
     fft16<false>(va);
     fft16<false>(vb);
@@ -373,9 +425,14 @@ __global__ void __launch_bounds__(kR16Threads, 3) frontend_r16_kernel(const Fron
         zk = make_float2(j0 ? k_self.x : k_reg.x, j0 ? k_self.y : k_reg.y);
         zp = vb[pos16(15 - e)];
       }
+#if KTF_R16_TW2_DERIVED
       // t = -i W_512^k, k = j + 16 e (lane 0: 16 e, then 8 + 16 e): the lane's base twiddle times the constant -i W_32^e
       const float2 t = cmul(e < 8 ? make_float2(tw2.x, tw2.y) : make_float2(tw2.z, tw2.w),
                             make_float2(-kSin32[e], -kCos32[e]));
+#else
+      const float4 t4 = t2[e >> 1];
+      const float2 t = (e & 1) ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y);
+#endif
       const float2 S = fma2(zp, make_float2(1.0f, -1.0f), zk);    // zk + conj(zp)
       const float2 D = fma2(zp, make_float2(-1.0f, 1.0f), zk);    // zk - conj(zp)
       const float2 G = cmul(D, t);
@@ -694,12 +751,24 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
   }
 
   const double PI = 3.14159265358979323846;
+#if KTF_R16_TW1_DERIVED
   for (int j = 0; j < 8; ++j)
     for (int k1 = 0; k1 < 16; ++k1) {
       const double th = -2.0 * PI * (double)((2 * j * k1) % 256) / 256.0;
       blob[kOffTw1 + j * kTw1Stride + k1 * 2] = (float)cos(th);
       blob[kOffTw1 + j * kTw1Stride + k1 * 2 + 1] = (float)sin(th);
     }
+#else
+  for (int j = 0; j < 8; ++j)
+    for (int k1 = 0; k1 < 16; ++k1)
+      for (int h = 0; h < 2; ++h) {
+        const int n2 = 2 * j + h;
+        const double th = -2.0 * PI * (double)((n2 * k1) % 256) / 256.0;
+        blob[kOffTw1 + j * kTw1Stride + k1 * 4 + 2 * h] = (float)cos(th);
+        blob[kOffTw1 + j * kTw1Stride + k1 * 4 + 2 * h + 1] = (float)sin(th);
+      }
+#endif
+#if KTF_R16_TW2_DERIVED
   for (int j = 0; j < 8; ++j) {   // W_512^k of the lane's first column for e < 8 and e >= 8
     const int k_lo = j, k_hi = (j == 0) ? 8 : j;
     blob[kOffTw2 + j * kTw2Stride + 0] = (float)cos(2.0 * PI * k_lo / 512.0);
@@ -707,6 +776,16 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
     blob[kOffTw2 + j * kTw2Stride + 2] = (float)cos(2.0 * PI * k_hi / 512.0);
     blob[kOffTw2 + j * kTw2Stride + 3] = (float)(-sin(2.0 * PI * k_hi / 512.0));
   }
+#else
+  for (int j = 0; j < 8; ++j)
+    for (int e = 0; e < 16; ++e) {
+      int k = j + 16 * e;
+      if (j == 0) k = e < 8 ? 16 * e : 8 + 16 * e;
+      const double th = 2.0 * PI * (double)k / 512.0;   // -i * exp(-i th) = (-sin th, -cos th)
+      blob[kOffTw2 + j * kTw2Stride + e * 2] = (float)(-sin(th));
+      blob[kOffTw2 + j * kTw2Stride + e * 2 + 1] = (float)(-cos(th));
+    }
+#endif
   fe->r16_dct_sym = 0;
   if (c.output == KTF_OUT_MFCC) {
     float* dp = blob.data() + kOffUnits + 8 * SD + 8 * SW;

@@ -350,3 +350,30 @@ def test_mfcc_full_size_batch_invariance(ktf):
         assert torch.equal(solo[0], out[b])
     ora = O.mfcc(O.framing(wav[7:8].cpu().numpy(), 25, 10, 16000), num_mfccs=30, num_mels=30, precise=True)
     assert np.max(np.abs(out[7].cpu().numpy() - ora[0])) < ABS_TOL_LOG_FEATURES
+
+
+@pytest.mark.parametrize("num_mels,num_mfccs", [(30, 30), (23, 13), (31, 20), (40, 23)])
+def test_mfcc_dct_paths_vs_oracle(ktf, fe, monkeypatch, num_mels, num_mfccs):
+    # The fast front-end has three DCT back-ends: the half-size register DCT (mirror-symmetric DCT-II, <= 32 mel
+    # bins, even and odd counts), the full register DCT (any other matrix) and the shared-memory table (> 32 bins).
+    # All three must agree with the float64 oracle; the non-symmetric path is forced with a perturbed matrix.
+    from kaldi_tflite_b200.layers import dsp
+    wav = fe["wav_trimmed"].astype(np.float32)[None]
+    kw = dict(num_mfccs=num_mfccs, num_mels=num_mels, use_energy=False)
+    frames = O.framing(wav, 25, 10, 16000)
+    truth = O.mfcc(frames, precise=True, **kw)[0]
+    fr = ktf.layers.Framing(dynamic_input_shape=True)
+    got = ktf.layers.MFCC(**kw)(fr(wav))[0]
+    assert np.max(np.abs(got - truth)) < ABS_TOL_LOG_FEATURES
+    assert np.quantile(np.abs(got - truth), 0.999) < P999_TOL_LOG_FEATURES
+
+    # a matrix without the mirror symmetry: out = logmel @ (D + E) differs from the symmetric result by logmel @ E
+    rng = np.random.default_rng(5)
+    pert = (rng.standard_normal((num_mels, num_mfccs)) * 1e-2).astype(np.float32)
+    real = dsp.dct2_matrix
+    monkeypatch.setattr(dsp, "dct2_matrix", lambda n_in, n_out: np.ascontiguousarray(real(n_in, n_out) + pert))
+    got2 = ktf.layers.MFCC(**kw)(fr(wav))[0]
+    logmel = O.filterbank(O.windowing(frames, return_energy=False, precise=True), precise=True, num_bins=num_mels)[0]
+    lift = O.lifter_coeffs(num_mfccs, 22)
+    want2 = truth + (logmel @ pert.astype(np.float64)) * lift
+    assert np.max(np.abs(got2 - want2)) < 2 * ABS_TOL_LOG_FEATURES
