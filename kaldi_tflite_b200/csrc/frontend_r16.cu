@@ -183,6 +183,39 @@ __device__ __forceinline__ void fft16(float2 (&x)[16]) {
   dft4(x[12], x[13], x[14], x[15]);
 }
 
+// K consecutive mel units of one schedule row: descriptors (first bin | filter slot << 16, keep flag), then the 2 K
+// power chunks and 2 K weight chunks, all loaded before the first product.  `u` is a multiple of 4.
+template <int K>
+__device__ __forceinline__ void mel_trip(int u, const int4* udesc4, const float4* uwts, const float* mel_tile,
+                                         float* mel_acc, float& run, float& keep) {
+  const int4 da = udesc4[u >> 1];
+  int4 db = make_int4(0, 0, 0, 0);
+  if (K > 2) db = udesc4[(u >> 1) + 1];
+  const int dx[4] = {da.x, da.z, db.x, db.z};
+  const float kp[4] = {__int_as_float(da.y), __int_as_float(da.w), __int_as_float(db.y), __int_as_float(db.w)};
+  float4 q0[K], q1[K], w0[K], w1[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) {
+    const float* q = mel_tile + (dx[t] & 0xffff);
+    q0[t] = *reinterpret_cast<const float4*>(q);
+    q1[t] = *reinterpret_cast<const float4*>(q + 4);
+    w0[t] = uwts[2 * (u + t)];
+    w1[t] = uwts[2 * (u + t) + 1];
+  }
+#pragma unroll
+  for (int t = 0; t < K; ++t) {
+    float2 acc0 = mul2(make_float2(w0[t].x, w0[t].y), make_float2(q0[t].x, q0[t].y));
+    float2 acc1 = mul2(make_float2(w1[t].x, w1[t].y), make_float2(q1[t].x, q1[t].y));
+    acc0 = fma2(make_float2(w0[t].z, w0[t].w), make_float2(q0[t].z, q0[t].w), acc0);
+    acc1 = fma2(make_float2(w1[t].z, w1[t].w), make_float2(q1[t].z, q1[t].w), acc1);
+    acc0 = add2(acc0, acc1);
+    // the only serial dependency between units: keep = 1 inside a filter, 0 after its last unit
+    run = fmaf(run, keep, acc0.x + acc0.y);
+    keep = kp[t];
+    mel_acc[dx[t] >> 16] = run;   // partial sums are overwritten by the filter's last unit (same lane, program order)
+  }
+}
+
 // DCT_REG 1 / 2 (MFCC with <= 32 mel bins): lane c keeps column c of the DCT matrix in registers and produces cepstrum
 // c of all 4 frames, so the DCT reads no table at all (only broadcast loads of the log-mel rows).
 // PCM16: the input is int16 PCM; the span buffer holds the raw 16-bit samples (half the HBM / L2 / smem bytes) and
@@ -454,33 +487,17 @@ __global__ void __launch_bounds__(kR16Threads, KTF_R16_MINB) frontend_r16_kernel
 
     // ---- mel bank (filterbank.py:238-240): lane (mf, mj) walks the NU units (8 bins each) of schedule row mj on frame
     //      mf; the units of a filter are consecutive on one row, the running sum is flushed at the filter's last unit.
-    //      Four units per trip (the host pads every row to a multiple of four with zero-weight units): all 18 loads of
-    //      a trip are in flight before the first product, instead of a descriptor -> address -> data chain per unit.
+    //      Four units per trip: all 18 loads of a trip are in flight before the first product, instead of a
+    //      descriptor -> address -> data chain per unit.
     float run = 0.0f, keep = 0.0f;
-    for (int u = 0; u < NU; u += 4) {
-      const int4 da = udesc4[u >> 1], db = udesc4[(u >> 1) + 1];   // (first bin | filter slot << 16, keep) x 4
-      const int dx[4] = {da.x, da.z, db.x, db.z};
-      const float kp[4] = {__int_as_float(da.y), __int_as_float(da.w), __int_as_float(db.y), __int_as_float(db.w)};
-      float4 q0[4], q1[4], w0[4], w1[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float* q = mel_tile + (dx[t] & 0xffff);
-        q0[t] = *reinterpret_cast<const float4*>(q);
-        q1[t] = *reinterpret_cast<const float4*>(q + 4);
-        w0[t] = uwts[2 * (u + t)];
-        w1[t] = uwts[2 * (u + t) + 1];
-      }
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        float2 acc0 = mul2(make_float2(w0[t].x, w0[t].y), make_float2(q0[t].x, q0[t].y));
-        float2 acc1 = mul2(make_float2(w1[t].x, w1[t].y), make_float2(q1[t].x, q1[t].y));
-        acc0 = fma2(make_float2(w0[t].z, w0[t].w), make_float2(q0[t].z, q0[t].w), acc0);
-        acc1 = fma2(make_float2(w1[t].z, w1[t].w), make_float2(q1[t].z, q1[t].w), acc1);
-        acc0 = add2(acc0, acc1);
-        // the only serial dependency between units: keep = 1 inside a filter, 0 after its last unit
-        run = fmaf(run, keep, acc0.x + acc0.y);
-        keep = kp[t];
-        mel_acc[dx[t] >> 16] = run;   // partial sums are overwritten by the filter's last unit (same lane, program order)
+    {
+      int u = 0;
+      for (; u + 4 <= NU; u += 4) mel_trip<4>(u, udesc4, uwts, mel_tile, mel_acc, run, keep);
+      switch (NU - u) {   // warp-uniform remainder, each size fully unrolled (predicating a 4-unit trip spills)
+        case 3: mel_trip<3>(u, udesc4, uwts, mel_tile, mel_acc, run, keep); break;
+        case 2: mel_trip<2>(u, udesc4, uwts, mel_tile, mel_acc, run, keep); break;
+        case 1: mel_trip<1>(u, udesc4, uwts, mel_tile, mel_acc, run, keep); break;
+        default: break;
       }
     }
     __syncwarp();
@@ -720,7 +737,6 @@ int r16_build(ktf_frontend* fe, const float* window_host, const float* mel_bank_
   }
   int NU = 1;
   for (int l = 0; l < 8; ++l) NU = std::max(NU, load[l]);
-  NU = (NU + 3) & ~3;   // the kernel walks four units per trip (a partial last trip costs more than the padding)
 
   // descriptors are read four at a time (the last trip may be partial: pad them to a multiple of four)
   const int SD = pad4mod32(2 * ((NU + 3) & ~3)), SW = pad4mod32(8 * NU);
