@@ -400,6 +400,9 @@ class Harness:
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION prints
+            # "NCCL version ..." to stdout) goes to stderr
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
         self.args = args
         self.flush_buf = None

@@ -26,7 +26,10 @@ def as_device(x, dtype=torch.float32):
     if isinstance(x, torch.Tensor):
         t = x
     elif isinstance(x, np.ndarray):
-        t = torch.from_numpy(np.ascontiguousarray(x))
+        x = np.ascontiguousarray(x)
+        if not x.flags.writeable:   # e.g. np.frombuffer views of a wav file: torch wants a writable buffer
+            x = x.copy()
+        t = torch.from_numpy(x)
     elif hasattr(x, "__dlpack__"):
         t = torch.from_dlpack(x)
     else:
