@@ -258,6 +258,7 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int dim, const long lo
 // every load in flight at once), and then slides the window out of shared memory.  The arithmetic (four partial sums
 // for the first window, add-new / subtract-old afterwards) is the one of cmvn_kernel.
 constexpr int kCmvnStagedWarps = 8;
+constexpr int kCmvnBlk = 32;   // rows per block sum
 
 template <bool NORM_VARS>
 __global__ void __launch_bounds__(kCmvnStagedWarps * 32)
@@ -328,29 +329,66 @@ cmvn_staged_kernel(const float* __restrict__ in, int dim, const long long* __res
   }
   __syncthreads();
 
+  // Column sums of the staged rows in blocks of kCmvnBlk: a warp's first window (N rows) is then a handful of block
+  // sums plus the rows that stick out on both sides, instead of N dependent loads and adds per column.
+  const float* xs = sbase - (long long)lo * dim;   // xs[t * dim + d] == x[t * dim + d] for lo <= t < hi
+  const int nblk = (hi - lo) / kCmvnBlk;
+  float* bsum = sx + (((size_t)(tc + N) * dim + 4 + 3) & ~(size_t)3);   // [nblk][dim] (+ [nblk][dim] of squares)
+  float* bsq = bsum + (size_t)((tc + N) / kCmvnBlk + 1) * dim;
+  for (int k = warp; k < nblk; k += kCmvnStagedWarps) {
+    for (int d = lane; d < dim; d += 32) {
+      const float* col = xs + (long long)(lo + k * kCmvnBlk) * dim + d;
+      float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+#pragma unroll
+      for (int r = 0; r < kCmvnBlk; r += 4) {
+        const float v0 = col[r * dim], v1 = col[(r + 1) * dim], v2 = col[(r + 2) * dim], v3 = col[(r + 3) * dim];
+        p0 += v0; p1 += v1; p2 += v2; p3 += v3;
+        if (NORM_VARS) {
+          q0 += __fmul_rn(v0, v0); q1 += __fmul_rn(v1, v1); q2 += __fmul_rn(v2, v2); q3 += __fmul_rn(v3, v3);
+        }
+      }
+      bsum[k * dim + d] = (p0 + p1) + (p2 + p3);
+      if (NORM_VARS) bsq[k * dim + d] = (q0 + q1) + (q2 + q3);
+    }
+  }
+  __syncthreads();
+
   const int per = (c1 - c0 + kCmvnStagedWarps - 1) / kCmvnStagedWarps;
   const int t0 = c0 + warp * per, t1 = min(t0 + per, c1);
   if (t0 >= t1) return;
-  const float* xs = sbase - (long long)lo * dim;   // xs[t * dim + d] == x[t * dim + d] for lo <= t < hi
   const float inv_n = 1.0f / (float)N;
   const int H = N / 2;
   for (int d = lane; d < dim; d += 32) {
     int ws = min(max(t0 - H, 0), T - N);
     float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f, q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
     {
-      const float* col = xs + ws * dim + d;
-      int k = 0;
-      for (; k + 4 <= N; k += 4) {
-        const float v0 = col[k * dim], v1 = col[(k + 1) * dim], v2 = col[(k + 2) * dim], v3 = col[(k + 3) * dim];
-        p0 += v0; p1 += v1; p2 += v2; p3 += v3;
-        if (NORM_VARS) {
-          q0 += __fmul_rn(v0, v0); q1 += __fmul_rn(v1, v1); q2 += __fmul_rn(v2, v2); q3 += __fmul_rn(v3, v3);
+      // rows [ws, ws + N) = leading rows up to the next block boundary, whole blocks, trailing rows
+      const int a0 = ws - lo;
+      const int kb = (a0 + kCmvnBlk - 1) / kCmvnBlk;
+      const int ke = min((a0 + N) / kCmvnBlk, nblk);
+      int r_lead_end = ws + N, r_trail = ws + N;       // no whole block inside: everything is "leading"
+      if (ke > kb) {
+        r_lead_end = lo + kb * kCmvnBlk;
+        r_trail = lo + ke * kCmvnBlk;
+        int k = kb;
+        for (; k + 2 <= ke; k += 2) {
+          p0 += bsum[k * dim + d]; p1 += bsum[(k + 1) * dim + d];
+          if (NORM_VARS) { q0 += bsq[k * dim + d]; q1 += bsq[(k + 1) * dim + d]; }
+        }
+        if (k < ke) {
+          p0 += bsum[k * dim + d];
+          if (NORM_VARS) q0 += bsq[k * dim + d];
         }
       }
-      for (; k < N; ++k) {
-        const float v = col[k * dim];
-        p0 += v;
-        if (NORM_VARS) q0 += __fmul_rn(v, v);
+      for (int r = ws; r < r_lead_end; ++r) {
+        const float v = xs[(long long)r * dim + d];
+        p2 += v;
+        if (NORM_VARS) q2 += __fmul_rn(v, v);
+      }
+      for (int r = r_trail; r < ws + N; ++r) {
+        const float v = xs[(long long)r * dim + d];
+        p3 += v;
+        if (NORM_VARS) q3 += __fmul_rn(v, v);
       }
     }
     float s = (p0 + p1) + (p2 + p3), s2 = (q0 + q1) + (q2 + q3);
@@ -456,7 +494,9 @@ int ktf_cmvn_forward(const float* in_dev, int32_t dim, const int64_t* frame_offs
   {
     // staged kernel when a CTA's rows fit in shared memory with >= 2 CTAs per SM
     const int tc = 256;
-    const size_t smem = ((size_t)(tc + window) * dim + 4) * sizeof(float);
+    // staged rows, then the block sums (and block sums of squares)
+    const size_t smem = ((((size_t)(tc + window) * dim + 4 + 3) & ~(size_t)3) +
+                         2 * (size_t)((tc + window) / kCmvnBlk + 1) * dim) * sizeof(float);
     const long long gys = (max_frames + tc - 1) / tc;
     if (smem <= 113 * 1024 && gys <= 65535) {
       static bool attr_set = false;
