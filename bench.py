@@ -378,7 +378,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": WORKLOAD_UNIT[w], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_json(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -400,9 +400,6 @@ class Harness:
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION prints
-            # "NCCL version ..." to stdout) goes to stderr
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
         self.args = args
         self.flush_buf = None
@@ -732,9 +729,31 @@ def run_ours(args):
     if h.rank == 0:
         if h.world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, 1)           # bounded sample, 1 thread, rank 0, N = 1 only
-        print(json.dumps(line))
+        emit_json(line)
     if h.world > 1:
         h.dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write there too (NCCL_DEBUG=VERSION prints its banner to
+    stdout and ignores NCCL_DEBUG_FILE at that level), so file descriptor 1 is pointed at stderr for the whole run
+    and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -747,6 +766,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
