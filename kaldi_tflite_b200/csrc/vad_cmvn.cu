@@ -493,11 +493,13 @@ int ktf_cmvn_forward(const float* in_dev, int32_t dim, const int64_t* frame_offs
   if (batch <= 0 || total_frames <= 0 || max_frames <= 0) return KTF_OK;
   {
     // staged kernel when a CTA's rows fit in shared memory with >= 2 CTAs per SM
-    const int tc = 256;
-    // staged rows, then the block sums (and block sums of squares)
+    // up to 256 frames per CTA, balanced over the longest utterance (998 frames -> 4 x 250: one CTA more per SM
+    // than 3 x 256 + 230 because the shared memory of 250 + window rows fits four times)
+    const long long gys = (max_frames + 255) / 256;
+    const int tc = (int)((((max_frames + gys - 1) / gys) + 1) & ~1LL);
+    // staged rows, then the block sums (and, for norm_vars, the block sums of squares)
     const size_t smem = ((((size_t)(tc + window) * dim + 4 + 3) & ~(size_t)3) +
-                         2 * (size_t)((tc + window) / kCmvnBlk + 1) * dim) * sizeof(float);
-    const long long gys = (max_frames + tc - 1) / tc;
+                         (norm_vars ? 2 : 1) * (size_t)((tc + window) / kCmvnBlk + 1) * dim) * sizeof(float);
     if (smem <= 113 * 1024 && gys <= 65535) {
       static bool attr_set = false;
       if (!attr_set) {
