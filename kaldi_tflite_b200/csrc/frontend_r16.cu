@@ -13,11 +13,18 @@
 //     power spectrum is produced without any further exchange.  Lane 0's two self-paired columns use
 //     the same instruction stream with a handful of selects (no divergent path), the Nyquist bin is
 //     never computed (its mel weight is identically zero, filterbank.py:176-187).
+//   * all complex arithmetic runs on packed FP32 pairs (add/sub/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2, sm_100):
+//     one issue slot per complex add, two per complex multiply; the half-swap / per-half-negate / broadcast operand
+//     modifiers of the packed SASS forms absorb the shuffles a complex product needs.
 //   * every shared-memory address is "per-lane base + immediate"; runtime configuration that the old
 //     kernel tested per frame is a template parameter or folded into the tables (lifter into the DCT
 //     matrix, the 1/4 of the untangling into the mel weights).
-//   * the mel filters are distributed over the 8 lanes of a frame by a host-side longest-first
-//     schedule, so the lanes' chunk counts are balanced.
+//   * mel bank: the phase re-maps lanes so that a quarter-warp (the conflict domain of LDS.128) holds schedule rows
+//     2q, 2q+1 of all 4 frames; even rows only read even 4-bin chunks, odd rows odd ones (host schedule), and the frame
+//     tiles sit 2 bank groups apart, so every power-tile load is bank-conflict free by construction.  Four units per
+//     trip, all loads in flight before the first product.
+//   * DCT: for the mirror-symmetric DCT-II (checked on the host) lane c keeps 16 coefficients and reads the sums /
+//     differences of mirrored log-mel pairs; any other matrix uses 32 registers, > 32 mel bins a shared-memory table.
 #include <math.h>
 #include <string.h>
 
@@ -50,7 +57,7 @@ constexpr int kRowStride = 36;        // floats per [k1] row of the exchange til
 constexpr int kTile = 584;            // floats per frame tile (16 * 36 = 576, +8 so that frames shift by 8 banks)
 constexpr int kOffWin = 0;
 // per-lane table rows are padded to a stride of 4 (mod 32) floats: the 8 lanes of a frame (one LDS.128
-// quarter-warp) then read 8 different bank groups
+// quarter-warp) then read 8 different bank groups.
 // Twiddles: read from exactly rounded per-lane tables (0), or derived in the kernel from a smaller table and
 // compile-time constants (1: fewer LDS bytes and registers, but two more roundings per twiddle, which shows on mel
 // bins 60 dB below the frame peak).
