@@ -488,7 +488,7 @@ def stage_tdnn(h, steps, warmup):
 def stage_wav2xvec(h, steps, warmup, batch=BATCH):
     import kaldi_tflite_b200 as ktf
     torch = h.torch
-    ext = ktf.models.XvectorExtractor(extractor_cfg(), precision="bf16", seed=0)
+    ext = ktf.models.XvectorExtractor(extractor_cfg(), precision="bf16", seed=0, allow_random_init=True)
     wav = gated_noise_cuda(batch, 7 + h.rank, h.dev)
     _, inter = ext(wav, return_intermediate=True)
     kept = int(inter["voiced_offsets"][-1].item())

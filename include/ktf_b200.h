@@ -14,8 +14,11 @@
  *     the caller (the Python host lets torch allocate them); `*_host` are host pointers.
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all work is
  *     enqueued asynchronously on it, nothing synchronises.
- *   - handles own only constant tables / packed weights on the device on which they
- *     were created; they are immutable after creation and may be shared by threads.
+ *   - handles own constant tables / packed weights on the device on which they were created.
+ *     ktf_frontend handles are immutable after creation and may be shared by threads.  ktf_affine
+ *     handles created with KTF_PREC_BF16, ktf_tdnn_stack and float32 ktf_plda handles additionally own a grow-only
+ *     device workspace that forward calls write: ONE such handle serves one stream / thread at a
+ *     time (create one handle per stream for concurrent use).
  *   - tensors are row-major, innermost dimension contiguous; float32 unless stated.
  *   - there is no CPU fallback anywhere in this library.
  */
@@ -153,6 +156,8 @@ int ktf_vad_mask(const ktf_vad_cfg* cfg, const float* feats_dev, int32_t dim,
  *   out_feats_dev (>= kept frames, dim) may be NULL to skip the gather.
  * workspace_dev must hold ktf_vad_compact_workspace(batch, total_frames) bytes. */
 int64_t ktf_vad_compact_workspace(int64_t batch, int64_t total_frames);
+/* The kept-row count stays on the device (out_offsets_dev[batch]); index_dev / out_feats_dev hold that many
+ * meaningful rows. */
 int ktf_vad_compact(const float* feats_dev, int32_t dim, const float* mask_dev,
                     const int64_t* frame_offsets_dev, int64_t batch, int64_t total_frames,
                     int64_t* out_offsets_dev, int64_t* index_dev, float* out_feats_dev,
@@ -208,6 +213,11 @@ int64_t ktf_affine_out_rows(const ktf_affine* a, int64_t T);
 
 /* x_dev (total_in_rows, D); utterance b = rows in_offsets_dev[b]..[b+1); output rows follow
  * out_offsets_dev (for SAME padding and subsampling 1 the two arrays are identical).
+ * total_in_rows / total_out_rows may be UPPER BOUNDS of in_offsets_dev[batch] / out_offsets_dev[batch]
+ * (they size grids and scratch; the offsets are read on the device), so a VAD-compacted batch needs no
+ * host round trip for its kept-row count; rows past the actual count are then undefined in y_dev.
+ * Both precisions support every mode of the reference layer: KTF_PREC_BF16 runs padding="VALID" and
+ * subsampling_factor > 1 (tdnn.py:224-249) as a splice of the evaluated time steps + one tcgen05 GEMM.
  * y_dev (total_out_rows, U) may be NULL when only statistics are wanted.
  * stats_dev, if not NULL, is (batch, 2, U) float32 and receives sum_t y and sum_t y^2 per
  * utterance (it is zeroed by this call). */
@@ -231,6 +241,8 @@ int ktf_tdnn_stack_create(ktf_affine* const* layers, int32_t num_layers, int32_t
 void ktf_tdnn_stack_destroy(ktf_tdnn_stack* s);
 int32_t ktf_tdnn_stack_out_dim(const ktf_tdnn_stack* s);
 /* feats_dev (total_rows, D0) fp32, utterance b = rows offsets_dev[b]..[b+1) (device int64, batch+1).
+ * total_rows may be an UPPER BOUND of offsets_dev[batch] (see ktf_affine_forward): every per-frame kernel
+ * reads the actual row count on the device.
  * out_dev: (batch, out_dim) fp32 when the stack pools over time, else (total_rows, out_dim). */
 int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int64_t* offsets_dev,
                            int64_t batch, int64_t total_rows, float* out_dev, void* stream);

@@ -43,16 +43,46 @@ void count_launch(int n = 1);
     }                                                                               \
   } while (0)
 
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs).
 inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cache[dev] == 0) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
+
+// True the first time it is called for (tag, current device): function attributes such as the dynamic shared-memory
+// limit are per device, so "set once" guards must be keyed on the device as well.
+inline bool first_use_on_device(unsigned long long* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
+// Stream-ordered scratch that is released on every exit path of the call that took it (early error returns included).
+struct Scratch {
+  cudaStream_t st;
+  void* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+  int n = 0;
+  explicit Scratch(cudaStream_t s) : st(s) {}
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  ~Scratch() {
+    for (int i = 0; i < n; ++i)
+      if (ptrs[i]) cudaFreeAsync(ptrs[i], st);
+  }
+  template <typename T>
+  cudaError_t take(T** p, size_t bytes);
+};
 
 // Stream-ordered scratch allocation.  The device's default memory pool is told to keep freed
 // blocks (release threshold = max) on first use: with the driver default (0) every stream / event
@@ -70,6 +100,15 @@ inline cudaError_t malloc_async(void** p, size_t bytes, cudaStream_t st) {
     pooled_dev = dev;
   }
   return cudaMallocAsync(p, bytes, st);
+}
+
+template <typename T>
+inline cudaError_t Scratch::take(T** p, size_t bytes) {
+  void* q = nullptr;
+  const cudaError_t e = malloc_async(&q, bytes, st);
+  if (e == cudaSuccess && n < 4) ptrs[n++] = q;
+  *p = static_cast<T*>(q);
+  return e;
 }
 
 // Grow-only device workspace owned by a handle (handles own packed weights, tables and a

@@ -747,8 +747,9 @@ int ktf_frontend_forward_ragged_ex(const ktf_frontend* fe, const void* wav_dev, 
   int rc = set_ingest(fe, a, wav_dev, sample_format, snip_edges);
   if (rc != KTF_OK) return rc;
 
+  ktf::Scratch scratch(st);            // released on every exit path
   long long* dev = nullptr;
-  KTF_CUDA(ktf::malloc_async((void**)&dev, host.size() * sizeof(long long), st));
+  KTF_CUDA(scratch.take(&dev, host.size() * sizeof(long long)));
   KTF_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
   KTF_CUDA(cudaStreamSynchronize(st));  // `host` is pageable and dies at return
 
@@ -759,9 +760,7 @@ int ktf_frontend_forward_ragged_ex(const ktf_frontend* fe, const void* wav_dev, 
   a.group_offsets = dev + 2 * (batch + 1);
   a.batch = batch;
   a.total_groups = go[batch];
-  rc = dispatch(fe, a, st);
-  cudaFreeAsync(dev, st);
-  return rc;
+  return dispatch(fe, a, st);
 }
 
 int ktf_frontend_forward_ragged(const ktf_frontend* fe, const float* wav_dev, int64_t batch,

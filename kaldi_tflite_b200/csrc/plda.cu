@@ -198,8 +198,9 @@ template <typename T>
 int score_impl(const ktf_plda* p, const T* ut, int64_t nt, const T* ue, int64_t ne, T* scores, int64_t ld,
                cudaStream_t st) {
   const int dim = p->dim;
+  ktf::Scratch scratch(st);            // released on every exit path
   T* ab = nullptr;
-  KTF_CUDA(ktf::malloc_async((void**)&ab, (size_t)(nt + ne) * sizeof(T), st));
+  KTF_CUDA(scratch.take(&ab, (size_t)(nt + ne) * sizeof(T)));
   T* A = ab;
   T* B = ab + nt;
   plda_quad_kernel<T><<<(unsigned)((nt + 7) / 8), 256, 0, st>>>(ut, nt, dim, (const T*)p->d_wa,
@@ -213,7 +214,6 @@ int score_impl(const ktf_plda* p, const T* ut, int64_t nt, const T* ue, int64_t 
   dim3 grid((unsigned)((nt + ktf::kTileM - 1) / ktf::kTileM), (unsigned)((ne + ktf::kTileN - 1) / ktf::kTileN));
   ktf::gemm_nt_kernel<T><<<grid, ktf::kGemmThreads, 0, st>>>((long long)nt, (long long)ne, dim, al, bl, epi);
   KTF_LAUNCH_OK();
-  KTF_CUDA(cudaFreeAsync(ab, st));
   return KTF_OK;
 }
 

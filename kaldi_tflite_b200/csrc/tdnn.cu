@@ -52,7 +52,7 @@ struct SpliceLoad {  // tdnn.py:244-247, 258: gather with edge clamp (SAME) or p
     const RowInfo ri = info[row];
     const int kc = k / D, d = k - kc * D;
     int t = ri.t_in + ctx[kc];
-    t = min(max(t, 0), ri.T - 1);
+    t = max(min(t, ri.T - 1), 0);      // rows past the last utterance (upper-bound row counts) stay in range
     return x[(ri.in_base + t) * D + d];
   }
 };
@@ -276,8 +276,9 @@ int ktf_affine_forward(const ktf_affine* a, const float* x_dev, const int64_t* i
                                   total_out_rows, y_dev, stats_dev, st);
 
   const int K = c.num_context * c.in_dim, U = c.out_dim;
+  ktf::Scratch scratch(st);            // released on every exit path
   RowInfo* info = nullptr;
-  KTF_CUDA(ktf::malloc_async((void**)&info, total_out_rows * sizeof(RowInfo), st));
+  KTF_CUDA(scratch.take(&info, total_out_rows * sizeof(RowInfo)));
   const int start = (c.padding_valid && c.context[0] < 0) ? -c.context[0] : 0;
   row_info_kernel<<<grid_for(total_out_rows, 256), 256, 0, st>>>(
       (const long long*)in_offsets_dev, (const long long*)out_offsets_dev, batch, total_out_rows, start,
@@ -285,7 +286,7 @@ int ktf_affine_forward(const ktf_affine* a, const float* x_dev, const int64_t* i
   KTF_LAUNCH_OK();
 
   float* y = y_dev;
-  if (y == nullptr) KTF_CUDA(ktf::malloc_async((void**)&y, (size_t)total_out_rows * U * sizeof(float), st));
+  if (y == nullptr) KTF_CUDA(scratch.take(&y, (size_t)total_out_rows * U * sizeof(float)));
 
   SpliceLoad al;
   al.x = x_dev;
@@ -304,8 +305,6 @@ int ktf_affine_forward(const ktf_affine* a, const float* x_dev, const int64_t* i
     stats_sum_kernel<<<g2, 128, 0, st>>>(y, (const long long*)out_offsets_dev, U, 1, stats_dev);
     KTF_LAUNCH_OK();
   }
-  if (y_dev == nullptr) KTF_CUDA(cudaFreeAsync(y, st));
-  KTF_CUDA(cudaFreeAsync(info, st));
   return KTF_OK;
 }
 
@@ -348,15 +347,15 @@ int ktf_stats_reduce(const float* x_dev, const int64_t* offsets_dev, int64_t bat
   KTF_CHECK_ARG(input_period > 0, "'input_period' and 'output_period' must be > 0");
   if (batch <= 0) return KTF_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  ktf::Scratch scratch(st);
   float* sums = nullptr;
-  KTF_CUDA(ktf::malloc_async((void**)&sums, (size_t)batch * 2 * dim * sizeof(float), st));
+  KTF_CUDA(scratch.take(&sums, (size_t)batch * 2 * dim * sizeof(float)));
   dim3 g((unsigned)batch, (unsigned)((dim + 127) / 128));
   stats_sum_kernel<<<g, 128, 0, st>>>(x_dev, (const long long*)offsets_dev, dim, input_period, sums);
   KTF_LAUNCH_OK();
   stats_finalize_kernel<<<g, 128, 0, st>>>(sums, (const long long*)offsets_dev, dim, include_std, epsilon,
                                            input_period, out_dev);
   KTF_LAUNCH_OK();
-  KTF_CUDA(cudaFreeAsync(sums, st));
   return KTF_OK;
 }
 

@@ -85,6 +85,9 @@ struct TcArgs {
   const void* act_base;     // activation matrix (the operand that streams from HBM), for the L2 prefetch
   long long act_ld_bytes;   // its row pitch and row count
   long long act_rows;
+  const long long* rows_dev;  // optional: the ACTUAL number of activation rows, read on the device (m_rows, or n_rows
+                              // when shift_b); the host value is then only an upper bound (VAD-compacted batches: no
+                              // host round trip for the kept-row count)
   int reverse;              // walk the tiles from the last row block to the first (see launch_gemm)
   int debug;                // development knobs (KTF_TC_DEBUG): 1 = skip global stores, 2 = skip the epilogue math
 };
@@ -322,8 +325,14 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   unsigned char* s_stg = smem + kStages * kStageBytes + 256 + kVecBytes + kSegBytes;    // [kEpiWarps][32][kStgPitch]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long m_tiles = (a.m_rows + BM - 1) / BM;
-  const int n_tiles = (int)((a.n_rows + BN - 1) / BN);
+  long long m_rows = a.m_rows, n_rows = a.n_rows;
+  if (a.rows_dev != nullptr) {
+    const long long actual = *a.rows_dev;
+    if (a.shift_b) n_rows = min(n_rows, actual); else m_rows = min(m_rows, actual);
+  }
+  const long long act_rows = a.rows_dev != nullptr ? (a.shift_b ? n_rows : m_rows) : a.act_rows;
+  const long long m_tiles = (m_rows + BM - 1) / BM;
+  const int n_tiles = (int)((n_rows + BN - 1) / BN);
   const long long total_tiles = m_tiles * n_tiles;
   const int num_kb = a.num_taps * a.kblocks_per_tap;
 
@@ -371,7 +380,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             long long r0 = (a.shift_b ? (long long)nt2 * BN : mt2 * BM) - kHalo;
             long long r1 = r0 + span + 2 * kHalo;
             r0 = r0 < 0 ? 0 : r0;
-            r1 = r1 > a.act_rows ? a.act_rows : r1;
+            r1 = r1 > act_rows ? act_rows : r1;
             if (r1 > r0)
               bulk_prefetch_l2(static_cast<const unsigned char*>(a.act_base) + r0 * a.act_ld_bytes,
                                (unsigned)((r1 - r0) * a.act_ld_bytes));
@@ -438,7 +447,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto prefetch_vec = [&](int nt_) {
       if (MODE != kModeStats && et < BN) {
         const int col = nt_ * BN + et;
-        const bool ok = col < a.n_rows;
+        const bool ok = col < n_rows;
         pre_b = (ok && a.bias) ? a.bias[col] : 0.0f;
         pre_s = (ok && a.scale) ? a.scale[col] : 1.0f;
         pre_o = (ok && a.offset) ? a.offset[col] : 0.0f;
@@ -462,9 +471,9 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int* seg = s_seg + acc * BN;
         if (et < BN) {
           const long long fr = (long long)col_base + et;
-          seg[et] = (fr < a.n_rows) ? a.rowseg[fr] : -1;
+          seg[et] = (fr < n_rows) ? a.rowseg[fr] : -1;
         }
-        const bool unit_ok = row < a.m_rows;
+        const bool unit_ok = row < m_rows;
         const float b = (unit_ok && a.bias) ? a.bias[row] : 0.0f;
         const float relu_lo = a.relu ? 0.0f : -3.402823466e+38f;
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
@@ -476,8 +485,8 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int cur = -1;
         auto flush = [&]() {
           if (cur >= 0 && unit_ok) {
-            atomicAdd(a.sums + ((long long)cur * 2 + 0) * a.m_rows + row, s);
-            atomicAdd(a.sums + ((long long)cur * 2 + 1) * a.m_rows + row, s2);
+            atomicAdd(a.sums + ((long long)cur * 2 + 0) * m_rows + row, s);
+            atomicAdd(a.sums + ((long long)cur * 2 + 1) * m_rows + row, s2);
           }
         };
         unsigned r[2][32];
@@ -539,15 +548,15 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         int flags = 0;
-        if (row < a.m_rows) flags = a.rowmap ? a.rowmap[row] : kRowStore;
+        if (row < m_rows) flags = a.rowmap ? a.rowmap[row] : kRowStore;
         if (a.debug & 1) flags = 0;
         const bool plain = __all_sync(0xffffffffu, flags == kRowStore);
         float radd = 0.0f;
-        if (MODE == kModeF32 && a.row_add != nullptr && row < a.m_rows) radd = a.row_add[row];
+        if (MODE == kModeF32 && a.row_add != nullptr && row < m_rows) radd = a.row_add[row];
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
 
-        const int n_cols = (int)a.n_rows;
+        const int n_cols = (int)n_rows;
         constexpr bool kBf16 = (MODE == kModeBf16);
         constexpr int kEs = kBf16 ? 2 : 4;                   // output element size
         const long long ld_bytes = a.out_ld * kEs;
@@ -630,11 +639,13 @@ __global__ void build_padded_kernel(const long long* __restrict__ offs, long lon
 template <typename TIn>
 __global__ void splice_kernel(const TIn* __restrict__ x, int D, long long x_ld, int x_is_padded,
                               const long long* __restrict__ offs, const long long* __restrict__ poffs,
-                              const int* __restrict__ rowseg, long long prow, int num_taps,
-                              const int* __restrict__ ctx_dev, __nv_bfloat16* __restrict__ out, long long ld) {
+                              const int* __restrict__ rowseg, long long prow, const long long* __restrict__ prow_dev,
+                              int num_taps, const int* __restrict__ ctx_dev, __nv_bfloat16* __restrict__ out,
+                              long long ld) {
   __shared__ int s_ctx[KTF_MAX_CONTEXT];
   if (threadIdx.x < KTF_MAX_CONTEXT) s_ctx[threadIdx.x] = threadIdx.x < num_taps ? ctx_dev[threadIdx.x] : 0;
   __syncthreads();
+  if (prow_dev != nullptr) prow = min(prow, *prow_dev);   // `prow` from the host is an upper bound
   const int chunks = (int)(ld >> 3);
   const long long total = prow * chunks;
   const int cols = num_taps * D;
@@ -671,7 +682,9 @@ __global__ void splice_kernel(const TIn* __restrict__ x, int D, long long x_ld, 
 // know about its row comes from rowmap / rowseg (two independent loads, no dependent chain through the offsets).
 __global__ void __launch_bounds__(256)
 splice_rows_kernel(const float* __restrict__ x, int D, const int* __restrict__ rowmap, const int* __restrict__ rowseg,
-                   long long prow, int K, int ctx0, __nv_bfloat16* __restrict__ out, long long ld) {
+                   long long prow, const long long* __restrict__ prow_dev, int K, int ctx0,
+                   __nv_bfloat16* __restrict__ out, long long ld) {
+  if (prow_dev != nullptr) prow = min(prow, *prow_dev);   // `prow` from the host is an upper bound
   const unsigned chunks = (unsigned)(ld >> 3);
   const int cols = K * D;
   const unsigned long long total = (unsigned long long)prow * chunks;
@@ -716,6 +729,48 @@ splice_rows_kernel(const float* __restrict__ x, int D, const int* __restrict__ r
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __float2bfloat16_rn(f[i]);
     *reinterpret_cast<uint4*>(out + p * ld + c0) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// Splice for the modes the padded-row layout does not cover -- padding="VALID" and subsampling_factor > 1
+// (tdnn.py:224-249): one output row per EVALUATED time step, out[r, k*D + d] = x[in_base + clamp(t_in + ctx_k), d] with
+// t_in = start + (r - out_offs[b]) * sub.  Rows map to utterances by binary search over out_offs (batch + 1).  Under
+// VALID padding every tap is in range by construction, so the clamp only acts for SAME (edge replication, :244-247).
+__global__ void __launch_bounds__(256)
+splice_eval_kernel(const float* __restrict__ x, int D, const long long* __restrict__ in_offs,
+                   const long long* __restrict__ out_offs, long long batch, long long out_rows, int start, int sub,
+                   int num_taps, const int* __restrict__ ctx_dev, __nv_bfloat16* __restrict__ out, long long ld) {
+  __shared__ int s_ctx[KTF_MAX_CONTEXT];
+  if (threadIdx.x < KTF_MAX_CONTEXT) s_ctx[threadIdx.x] = threadIdx.x < num_taps ? ctx_dev[threadIdx.x] : 0;
+  __syncthreads();
+  const int chunks = (int)(ld >> 3);
+  const long long total = out_rows * chunks;
+  const int cols = num_taps * D;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / chunks;
+    const int c0 = (int)(idx - r * chunks) << 3;
+    long long lo = 0, hi = batch;
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) >> 1;
+      if (out_offs[mid] <= r) lo = mid; else hi = mid;
+    }
+    const long long base = in_offs[lo];
+    const long long T = in_offs[lo + 1] - base;
+    const long long t = start + (r - out_offs[lo]) * sub;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      float f = 0.0f;
+      if (c < cols && T > 0) {
+        const int k = c / D, d = c - k * D;
+        const long long tt = min(max(t + s_ctx[k], 0LL), T - 1);
+        f = x[(base + tt) * D + d];
+      }
+      v[i] = __float2bfloat16_rn(f);
+    }
+    *reinterpret_cast<uint4*>(out + r * ld + c0) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
@@ -820,8 +875,7 @@ int encode_map(CUtensorMap* map, const void* base, unsigned long long inner, uns
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 int check_arch() {
-  static int arch = 0;
-  if (arch == 0) arch = ktf_device_arch();
+  const int arch = ktf_device_arch();                    // the current device's, not the first one's
   if (arch < 100) {
     ktf::set_error("the tcgen05 engine needs an sm_100 device (found sm_%d)", arch);
     return KTF_EINVAL;
@@ -861,11 +915,9 @@ void release_layer(TcLayer* L) {
 
 template <int MODE>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;              // per device (function attributes are per context)
+  if (ktf::first_use_on_device(&attr_done))
     KTF_CUDA(cudaFuncSetAttribute(tdnn_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc));
-    attr_done = true;
-  }
   const long long tiles = ((args.m_rows + BM - 1) / BM) * ((args.n_rows + BN - 1) / BN);
   if (tiles <= 0) return KTF_OK;
   static int dbg = -1;
@@ -898,7 +950,7 @@ void fill_taps(TcArgs& args, const TcLayer& L, bool a_is_spliced, long long a_co
 // (implicit taps) or an already spliced matrix.
 int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, long long a_ld, long long a_cols,
               long long m_rows, const int* rowmap, void* out, long long out_ld, bool out_bf16, bool a_is_spliced,
-              cudaStream_t st, int reverse = 0) {
+              cudaStream_t st, int reverse = 0, const long long* rows_dev = nullptr) {
   CUtensorMap tmA;
   int rc = encode_map(&tmA, A, (unsigned long long)a_cols, (unsigned long long)m_rows, (unsigned long long)a_ld, BK, BM);
   if (rc != KTF_OK) return rc;
@@ -909,6 +961,7 @@ int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, lon
   args.act_base = A;
   args.act_ld_bytes = a_ld * 2;
   args.act_rows = m_rows;
+  args.rows_dev = rows_dev;
   args.reverse = reverse;
   args.rowmap = rowmap;
   args.bias = a->d_bias;
@@ -924,7 +977,7 @@ int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, lon
 // per-utterance sum / sum of squares of relu(acc + bias) into sums (batch, 2, U) (pre-zeroed).
 int run_layer_stats(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* X, long long x_ld, long long x_cols,
                     long long frames, const int* rowseg, float* sums, bool x_is_spliced, cudaStream_t st,
-                    int reverse = 0) {
+                    int reverse = 0, const long long* rows_dev = nullptr) {
   CUtensorMap tmX;
   int rc = encode_map(&tmX, X, (unsigned long long)x_cols, (unsigned long long)frames, (unsigned long long)x_ld, BK, BN);
   if (rc != KTF_OK) return rc;
@@ -936,6 +989,7 @@ int run_layer_stats(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* 
   args.act_base = X;
   args.act_ld_bytes = x_ld * 2;
   args.act_rows = frames;
+  args.rows_dev = rows_dev;
   args.reverse = reverse;
   args.rowseg = rowseg;
   args.bias = a->d_bias;
@@ -979,18 +1033,18 @@ void affine_tc_release(ktf_affine* a) {
 
 // Materialises the spliced bf16 operand of a layer fed by fp32 ragged features.
 static int launch_splice_f32(const TcLayer& L, const float* x, const long long* offs, const long long* poffs,
-                      const int* rowmap, const int* rowseg, long long prow, __nv_bfloat16* out, long long ld,
-                      cudaStream_t st) {
+                      const int* rowmap, const int* rowseg, long long prow, const long long* prow_dev,
+                      __nv_bfloat16* out, long long ld, cudaStream_t st) {
   bool consecutive = (L.D % 2) == 0;
   for (int k = 1; k < L.K; ++k) consecutive = consecutive && (L.ctx[k] == L.ctx[0] + k);
   bool small = true;                       // contexts inside the halo (the edge distances saturate at 15)
   for (int k = 0; k < L.K; ++k) small = small && L.ctx[k] >= -kHalo && L.ctx[k] <= kHalo;
   if (consecutive && small) {
-    splice_rows_kernel<<<blocks_for(prow * (ld >> 3), 256), 256, 0, st>>>(x, L.D, rowmap, rowseg, prow, L.K, L.ctx[0],
-                                                                           out, ld);
+    splice_rows_kernel<<<blocks_for(prow * (ld >> 3), 256), 256, 0, st>>>(x, L.D, rowmap, rowseg, prow, prow_dev, L.K,
+                                                                           L.ctx[0], out, ld);
   } else {
     splice_kernel<float><<<blocks_for(prow * (ld >> 3), 256), 256, 0, st>>>(x, L.D, L.D, 0, offs, poffs, rowseg, prow,
-                                                                            L.K, L.d_ctx, out, ld);
+                                                                            prow_dev, L.K, L.d_ctx, out, ld);
   }
   KTF_LAUNCH_OK();
   return KTF_OK;
@@ -1000,12 +1054,32 @@ int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in
                       const int64_t* out_offsets_dev, int64_t batch, int64_t total_in_rows,
                       int64_t total_out_rows, float* y_dev, float* stats_dev, cudaStream_t st) {
   TcLayer& L = *static_cast<TcLayer*>(a->tc);
-  KTF_CHECK_ARG(!a->cfg.padding_valid && a->cfg.subsampling_factor == 1,
-                "KTF_PREC_BF16 supports padding=SAME, subsampling_factor=1 (use KTF_PREC_F32 otherwise)");
-  KTF_CHECK_ARG(total_in_rows == total_out_rows, "row count mismatch");
-  (void)out_offsets_dev;
-  const long long prow = total_in_rows + 2LL * kHalo * batch;
   const long long cols = (long long)L.K * L.D, ld = round_up(cols, 8);
+  int rc;
+  if (a->cfg.padding_valid || a->cfg.subsampling_factor != 1) {
+    // padding="VALID" / subsampling (tdnn.py:224-249): splice the evaluated time steps only, one plain GEMM over them
+    ktf::Carver cv;
+    const size_t o_spliced = cv.take((size_t)total_out_rows * ld * sizeof(__nv_bfloat16));
+    const size_t o_y = cv.take(y_dev ? 0 : (size_t)total_out_rows * L.U * sizeof(float));
+    if ((rc = L.ws.ensure(cv.off)) != KTF_OK) return rc;
+    char* base = static_cast<char*>(L.ws.ptr);
+    __nv_bfloat16* spliced = reinterpret_cast<__nv_bfloat16*>(base + o_spliced);
+    float* y = y_dev ? y_dev : reinterpret_cast<float*>(base + o_y);
+    const int start = (a->cfg.padding_valid && a->cfg.context[0] < 0) ? -a->cfg.context[0] : 0;
+    splice_eval_kernel<<<blocks_for(total_out_rows * (ld >> 3), 256), 256, 0, st>>>(
+        x_dev, L.D, (const long long*)in_offsets_dev, (const long long*)out_offsets_dev, batch, total_out_rows, start,
+        a->cfg.subsampling_factor, L.K, L.d_ctx, spliced, ld);
+    KTF_LAUNCH_OK();
+    if ((rc = run_layer(L, a, spliced, ld, cols, total_out_rows, nullptr, y, L.U, /*out_bf16=*/false, /*spliced=*/true,
+                        st)) != KTF_OK)
+      return rc;
+    if (stats_dev) return ktf::stats_sums_f32(y, out_offsets_dev, batch, L.U, stats_dev, st);
+    return KTF_OK;
+  }
+  KTF_CHECK_ARG(total_in_rows == total_out_rows, "row count mismatch");
+  // total_in_rows may be an upper bound of in_offsets_dev[batch] (VAD-compacted batches): the padded-row count is
+  // read back on the device (poffs[batch]) by the splice and the GEMM
+  const long long prow = total_in_rows + 2LL * kHalo * batch;
   ktf::Carver cv;
   const size_t o_poffs = cv.take((batch + 1) * sizeof(long long));
   const size_t o_rowmap = cv.take(prow * sizeof(int));
@@ -1013,7 +1087,7 @@ int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in
   const size_t o_spliced = cv.take((size_t)prow * ld * sizeof(__nv_bfloat16));
   const size_t o_yp = cv.take((size_t)prow * L.U * sizeof(float));
   const size_t o_y = cv.take(y_dev ? 0 : (size_t)total_out_rows * L.U * sizeof(float));
-  int rc = L.ws.ensure(cv.off);
+  rc = L.ws.ensure(cv.off);
   if (rc != KTF_OK) return rc;
   char* base = static_cast<char*>(L.ws.ptr);
   long long* poffs = reinterpret_cast<long long*>(base + o_poffs);
@@ -1025,9 +1099,11 @@ int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in
 
   build_padded_kernel<<<(unsigned)batch, 128, 0, st>>>((const long long*)in_offsets_dev, batch, poffs, rowmap, rowseg);
   KTF_LAUNCH_OK();
-  if ((rc = launch_splice_f32(L, x_dev, (const long long*)in_offsets_dev, poffs, rowmap, rowseg, prow, spliced, ld, st)) != KTF_OK)
+  if ((rc = launch_splice_f32(L, x_dev, (const long long*)in_offsets_dev, poffs, rowmap, rowseg, prow, poffs + batch,
+                              spliced, ld, st)) != KTF_OK)
     return rc;
-  rc = run_layer(L, a, spliced, ld, cols, prow, rowmap, yp, L.U, /*out_bf16=*/false, /*spliced=*/true, st);
+  rc = run_layer(L, a, spliced, ld, cols, prow, rowmap, yp, L.U, /*out_bf16=*/false, /*spliced=*/true, st, 0,
+                 poffs + batch);
   if (rc != KTF_OK) return rc;
   unpad_rows_kernel<<<(unsigned)batch, 256, 0, st>>>(yp, L.U, L.U, (const long long*)in_offsets_dev, poffs, batch, y);
   KTF_LAUNCH_OK();
@@ -1175,6 +1251,9 @@ int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int6
 
   build_padded_kernel<<<(unsigned)batch, 128, 0, st>>>(offs, batch, poffs, rowmap, rowseg);
   KTF_LAUNCH_OK();
+  // `total_rows` may be an upper bound of offsets_dev[batch]: the per-frame kernels read the actual padded-row count
+  // (poffs[batch], written by the kernel above) on the device, so a VAD-compacted batch needs no host round trip
+  const long long* prow_dev = poffs + batch;
 
   const __nv_bfloat16* cur = nullptr;   // current activations (bf16) and their geometry
   long long cur_ld = 0;
@@ -1208,10 +1287,11 @@ int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int6
       const long long ld = round_up(cols, 8);
       const unsigned grid = blocks_for(prow * (ld >> 3), 256);
       if (i == 0) {
-        if ((rc = ktf::launch_splice_f32(L, feats_dev, offs, poffs, rowmap, rowseg, prow, sp, ld, st)) != KTF_OK) return rc;
+        if ((rc = ktf::launch_splice_f32(L, feats_dev, offs, poffs, rowmap, rowseg, prow, prow_dev, sp, ld, st)) != KTF_OK)
+          return rc;
       } else {
-        splice_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(cur, L.D, cur_ld, 1, offs, poffs, rowseg, prow, L.K,
-                                                           L.d_ctx, sp, ld);
+        splice_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(cur, L.D, cur_ld, 1, offs, poffs, rowseg, prow, prow_dev,
+                                                           L.K, L.d_ctx, sp, ld);
         KTF_LAUNCH_OK();
       }
       A = sp;
@@ -1224,7 +1304,8 @@ int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int6
     if (i == s->stats_after) {
       // fused StatsPooling: the activation of this layer is never stored
       KTF_CUDA(cudaMemsetAsync(sums, 0, (size_t)batch * 2 * L.U * sizeof(float), st));
-      if ((rc = run_layer_stats(L, a, A, a_ld, a_cols, prow, rowseg, sums, spliced, st, i & 1)) != KTF_OK) return rc;
+      if ((rc = run_layer_stats(L, a, A, a_ld, a_cols, prow, rowseg, sums, spliced, st, i & 1, prow_dev)) != KTF_OK)
+        return rc;
       dim3 grid((unsigned)batch, (unsigned)((L.U + 127) / 128));
       stats_finalize_tc_kernel<<<grid, 128, 0, st>>>(sums, offs, L.U, a->d_scale, a->d_offset, s->include_std,
                                                      s->stats_eps, last ? nullptr : pooled, last ? out_dev : nullptr,
@@ -1237,7 +1318,8 @@ int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int6
     }
     if (last) {
       // per-frame fp32 output, un-padded into the caller's ragged layout
-      if ((rc = run_layer(L, a, A, a_ld, a_cols, prow, rowmap, yp, L.U, false, spliced, st)) != KTF_OK) return rc;
+      if ((rc = run_layer(L, a, A, a_ld, a_cols, prow, rowmap, yp, L.U, false, spliced, st, 0, prow_dev)) != KTF_OK)
+        return rc;
       unpad_rows_kernel<<<(unsigned)batch, 256, 0, st>>>(yp, L.U, L.U, offs, poffs, batch, out_dev);
       KTF_LAUNCH_OK();
       return KTF_OK;
@@ -1246,7 +1328,8 @@ int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int6
     const long long y_ld = round_up(L.U, 8);
     // serpentine: odd layers walk the row blocks backwards, starting on the rows the previous layer wrote
     // last (still L2 resident) instead of the ones it wrote first (long evicted when activations > L2)
-    if ((rc = run_layer(L, a, A, a_ld, a_cols, prow, rowmap, y, y_ld, true, spliced, st, i & 1)) != KTF_OK) return rc;
+    if ((rc = run_layer(L, a, A, a_ld, a_cols, prow, rowmap, y, y_ld, true, spliced, st, i & 1, prow_dev)) != KTF_OK)
+      return rc;
     cur = y;
     cur_ld = y_ld;
     which ^= 1;

@@ -501,11 +501,10 @@ int ktf_cmvn_forward(const float* in_dev, int32_t dim, const int64_t* frame_offs
     const size_t smem = ((((size_t)(tc + window) * dim + 4 + 3) & ~(size_t)3) +
                          (norm_vars ? 2 : 1) * (size_t)((tc + window) / kCmvnBlk + 1) * dim) * sizeof(float);
     if (smem <= 113 * 1024 && gys <= 65535) {
-      static bool attr_set = false;
-      if (!attr_set) {
+      static unsigned long long attr_set = 0;           // per device (function attributes are per context)
+      if (ktf::first_use_on_device(&attr_set)) {
         KTF_CUDA(cudaFuncSetAttribute(cmvn_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
         KTF_CUDA(cudaFuncSetAttribute(cmvn_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-        attr_set = true;
       }
       auto kern = norm_vars ? cmvn_staged_kernel<true> : cmvn_staged_kernel<false>;
       kern<<<dim3((unsigned)batch, (unsigned)gys), kCmvnStagedWarps * 32, smem, (cudaStream_t)stream>>>(

@@ -22,6 +22,7 @@ class Layer:
         self.trainable = trainable
         self.built = False
         self._build_shape = None
+        self._weights_version = 0   # bumped by set_weights(); fused plans that cached the old weights rebuild
 
     # keras semantics: build() runs once, the first time the layer sees an input shape.
     def build(self, input_shape):

@@ -602,7 +602,12 @@ class VAD(Layer):
 
     @staticmethod
     def compact_ragged(feats2d, mask, offsets, gather=True):
-        """Stable per-utterance compaction -> (kept feats or None, new offsets, row index)."""
+        """Stable per-utterance compaction -> (kept feats or None, new offsets, row index).
+
+        Nothing here synchronises with the host: the number of kept rows stays on the device (`new offsets[-1]`), the
+        returned `feats` / `index` buffers have the UPPER-BOUND length `rows` and only their first `new offsets[-1]`
+        entries are meaningful.  Every consumer on the hot path (CMVN, the TDNN stack) takes the per-utterance
+        offsets from the device, so wav -> x-vector can be captured in a CUDA graph."""
         rows, D = feats2d.shape
         B = offsets.numel() - 1
         out_offs = torch.empty((B + 1,), device=mask.device, dtype=torch.int64)
@@ -613,8 +618,7 @@ class VAD(Layer):
         N.check(N.lib().ktf_vad_compact(T.ptr(feats2d), D, T.ptr(mask), T.ptr(offsets), B, rows,
                                         T.ptr(out_offs), T.ptr(index), T.ptr(out), T.ptr(ws),
                                         T.stream_ptr()))
-        kept = int(out_offs[-1].item())
-        return (out[:kept] if gather else None), out_offs, index[:kept]
+        return out, out_offs, index
 
     def call(self, inputs):
         x = T.as_device(inputs)
@@ -625,6 +629,9 @@ class VAD(Layer):
         mask = self.mask_ragged(x.reshape(B * Tn, D), offsets)
         if not self.returnIndexes:
             return T.like_input(mask.reshape(B, Tn, 1), inputs)
-        _, _, index = self.compact_ragged(x.reshape(B * Tn, D), mask, offsets, gather=False)
+        _, out_offs, index = self.compact_ragged(x.reshape(B * Tn, D), mask, offsets, gather=False)
+        # tf.where returns a data-dependent shape (vad.py:200-203): this API -- unlike the fused wav -> x-vector
+        # path -- has to read the count back
+        index = index[:int(out_offs[-1].item())]
         idx = torch.stack([index // Tn, index % Tn], dim=1)        # (n_active, 2) like tf.where
         return T.like_input(idx, inputs)

@@ -134,6 +134,7 @@ class BatchNorm(Layer):
             raise ValueError(f"expected weights of dim {self._build_shape[-1]}, got {mean.shape[0]}")
         self.gamma, self.moving_mean, self.moving_variance = g, mean, var
         self._dev = None
+        self._weights_version += 1
 
     def scale_offset(self):
         """Inference BN folded to y = x * scale + offset (batchnorm.py:81-88, center=False)."""

@@ -16,8 +16,10 @@ from .base import Layer
 PRECISIONS = {"f32": N.KTF_PREC_F32, "fp32": N.KTF_PREC_F32, "float32": N.KTF_PREC_F32,
               "bf16": N.KTF_PREC_BF16, "bfloat16": N.KTF_PREC_BF16}
 
-# Operand precision of TDNN contractions when a layer does not say otherwise.
-DEFAULT_PRECISION = "f32"
+# Operand precision of TDNN contractions when a layer does not say otherwise: bf16 operands with fp32 accumulation on the
+# tcgen05 engine (BASELINE.json north_star: "x-vectors with cosine >= 0.9999 at TF32/bf16 TDNN precision").  "f32" selects
+# the exact fp32 SIMT tiles (the precision reference of the tests).
+DEFAULT_PRECISION = "bf16"
 
 
 def reshapeKaldiTdnnWeights(weights, units, kernel_width):
@@ -49,6 +51,7 @@ class _Affine:
         assert KD % K == 0
         self.in_dim, self.out_dim, self.context = KD // K, U, list(context)
         prec = PRECISIONS[(precision or DEFAULT_PRECISION).lower()]
+        self.bf16 = prec == N.KTF_PREC_BF16
         cfg = N.AffineCfg(in_dim=self.in_dim, out_dim=U, num_context=K, subsampling_factor=subsampling,
                           padding_valid=int(padding.upper() == "VALID"),
                           activation=N.KTF_ACT_RELU if relu else N.KTF_ACT_NONE, precision=prec)
@@ -236,6 +239,7 @@ class TDNN(Layer):
                 raise ValueError(f"unexpected bias shape {bias.shape}")
             self.bias = bias
         self._affine = None
+        self._weights_version += 1
 
     def kaldi_weights(self):
         return kernelToKaldi(self.kernel), self.bias

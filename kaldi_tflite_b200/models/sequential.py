@@ -58,6 +58,7 @@ class Sequential:
         self.dtype = "float32"
         self._plan = None
         self._stack = None
+        self._plan_version = None
         if input_shape is not None and input_shape[-1] is not None:
             self._build_layers(input_shape[-1])
 
@@ -78,8 +79,12 @@ class Sequential:
         raise ValueError(f"No such layer: {name}")
 
     def invalidate(self):
-        """Drop the fused plan (call after changing any layer's weights)."""
+        """Drop the fused plan.  Not needed after `layer.set_weights(...)`: every forward compares the layers' weight
+        versions with the ones the plan was built from (keras applies set_weights immediately; so does this)."""
         self._plan = None
+
+    def _weights_version(self):
+        return tuple(l._weights_version for l in self.layers)
 
     def _resolved_precision(self):
         from ..layers import tdnn as _t
@@ -90,7 +95,7 @@ class Sequential:
         from ..layers.tdnn import _Stack
         affines, stats_after, stats = [], -1, None
         for kind, obj, st in plan:
-            if kind != "affine" or not obj.same:
+            if kind != "affine" or not obj.same or not obj.bf16:
                 return None
             affines.append(obj)
             if st is not None:
@@ -133,12 +138,12 @@ class Sequential:
 
     def forward_ragged(self, x2d, offsets):
         """x2d CUDA (rows, D); utterance b = rows offsets[b]..offsets[b+1].  Returns (y2d, offsets)."""
-        if self._plan is None:
+        if self._plan is None or self._plan_version != self._weights_version():
             self._build_layers(x2d.shape[-1])
             self._plan = self._make_plan()
+            self._plan_version = self._weights_version()
             self._stack = None
-            if self._resolved_precision() in ("bf16", "bfloat16"):
-                self._stack = self._try_stack(self._plan)
+            self._stack = self._try_stack(self._plan)       # None unless every layer runs on the tcgen05 engine
         B = offsets.numel() - 1
         if self._stack is not None:
             y = self._stack.forward_ragged(x2d, offsets)

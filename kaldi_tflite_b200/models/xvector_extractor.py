@@ -7,8 +7,9 @@ Differences that do not change results for the reference's use (batch 1):
   * any batch is accepted: a (B, N) array, a 1-D (N,) array, or a list of 1-D arrays of
     different lengths (ragged).  Utterances are independent (the reference collapses the batch
     at tf.gather_nd, xvector_extractor.py:163-165, so it is batch-1 only).
-  * no network: when the Kaldi `final.raw` is absent the TDNN is randomly initialised with a
-    fixed seed and a warning is printed (the reference would download it, :55-65).
+  * no network: when the Kaldi `final.raw` named by the config is absent the constructor raises
+    FileNotFoundError (the reference would download it, :55-65).  Benchmarks and tests that only need the
+    ARCHITECTURE pass `allow_random_init=True` (seeded Glorot weights, recorded as `.randomInit`).
 """
 
 import os
@@ -44,16 +45,16 @@ def XvectorExtractorFromConfig(cfgPath: str, name: str = None, **kwargs):
              os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(cfgPath)), "..", ".."))]
     for key in ("model_config_path", "model_path", "global_mean_path", "lda_matrix_path"):
         ext["xvec"][key] = _resolve(ext["xvec"].get(key), bases)
-    if not os.path.exists(ext["xvec"]["model_path"] or ""):
-        warnings.warn(f"Kaldi model '{ext['xvec']['model_path']}' not found and there is no network to "
-                      "download it: the TDNN is randomly initialised (seed 0)")
     return XvectorExtractor(ext, name=name, **kwargs)
 
 
 class XvectorExtractor:
 
     def __init__(self, cfg: dict, name: str = None, chunk_size: int = 300, precision: str = None,
-                 seed: int = 0, dither: float = None):
+                 seed: int = 0, dither: float = None, allow_random_init: bool = False):
+        """`precision`: operand precision of the TDNN contractions ("bf16" = tcgen05 engine, the default; "f32" = exact
+        SIMT tiles).  `allow_random_init`: accept a missing Kaldi `final.raw` and initialise the TDNN with seeded Glorot
+        weights (x-vectors are then meaningless: benchmarks / architecture tests only)."""
         self.name = name
         self.chunkSize = chunk_size
         fr = dict(cfg["framing"])
@@ -68,8 +69,16 @@ class XvectorExtractor:
         with open(cfg["xvec"]["model_config_path"], "r") as f:
             nnet3Cfg = yaml.safe_load(f)
         model_path = cfg["xvec"].get("model_path")
-        if model_path is not None and not os.path.exists(model_path):
+        if model_path is None or not os.path.exists(model_path):
+            if not allow_random_init:
+                raise FileNotFoundError(
+                    f"Kaldi nnet3 model '{model_path}' not found (there is no network to download it, "
+                    "xvector_extractor.py:55-65); pass allow_random_init=True to run the architecture with seeded "
+                    "random weights")
+            warnings.warn(f"Kaldi model '{model_path}' not found: the TDNN is randomly initialised (seed {seed}); "
+                          "the x-vectors carry no speaker information")
             model_path = None
+        self.randomInit = model_path is None
         self.xvec = SequentialFromConfig(nnet3Cfg["model_config"], model_path, "cmvn2xvec",
                                          precision=precision, seed=seed)
 
@@ -100,6 +109,7 @@ class XvectorExtractor:
 
     def embed(self, feats, offsets, max_frames=None):
         mask = self.vad.mask_ragged(feats, offsets)
+        # `voiced` keeps the upper-bound row count; the kept-row count stays on the device (voffs[-1])
         voiced, voffs, _ = self.vad.compact_ragged(feats, mask, offsets, gather=True)
         # An utterance without voiced frames has no statistics to pool (the reference's gather_nd / reduce_mean
         # would produce NaN).  The flag stays on the device -- checking it here would stall the launch queue --

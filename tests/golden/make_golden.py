@@ -180,6 +180,12 @@ def main():
         TD, "tdnn", "src", "0008_sitw_v2_1a_tdnn6.affine", "output.ark.txt"))
     pack["sitw_e2e_xvector"] = stack_ark(os.path.join(
         TD, "models", "src", "0008_sitw_v2_1a", "xvector.ark.txt"))
+    # CALLHOME diarization model (8 kHz, 23-dim input, models/kaldi/sequential_test.py:78): its input chunk; the Kaldi
+    # output needs the un-vendored final.raw as well
+    pack["callhome_chunk_mfcc"] = stack_ark(os.path.join(
+        TD, "tdnn", "src", "0006_callhome_diarization_v2_1a_tdnn6.affine", "feat.ark.txt"))
+    pack["callhome_tdnn6_out"] = stack_ark(os.path.join(
+        TD, "tdnn", "src", "0006_callhome_diarization_v2_1a_tdnn6.affine", "output.ark.txt"))
     np.savez_compressed(os.path.join(OUT, "tdnn.npz"), **pack)
 
     np.savez_compressed(

@@ -27,7 +27,7 @@ def test_tdnn_single_layer_vs_kaldi(ktf):
     g = load_golden("tdnn.npz")
     cfg = json.loads(str(g["single_cfg"]))
     r = ktf.io.KaldiNnet3Reader(golden_path("tdnn_single_layer.final.raw"), True)
-    layer = ktf.layers.TDNN.from_config(cfg)
+    layer = ktf.layers.TDNN.from_config({**cfg, "precision": "f32"})   # the reference's 1e-6 is an fp32 tolerance
     layer.build(g["single_in"].shape)
     layer.set_weights([r.components[0]["params"], r.components[0]["bias"]])
     got = layer(g["single_in"])
@@ -41,13 +41,13 @@ def test_tdnn_narrow_vs_kaldi(ktf):
     r = ktf.io.KaldiNnet3Reader(golden_path("tdnn_narrow.final.raw"), True)
     layers = []
     for name, dim, ctx, use_relu, use_bn in helpers.NARROW_LAYERS:
-        l = ktf.layers.TDNN(dim, context=ctx, name=f"{name}.affine")
+        l = ktf.layers.TDNN(dim, context=ctx, name=f"{name}.affine", precision="f32")
         layers.append(l)
         if use_relu:
             layers.append(ktf.layers.ReLU(name=f"{name}.relu"))
         if use_bn:
             layers.append(ktf.layers.BatchNorm(name=f"{name}.batchnorm"))
-    mdl = ktf.models.Sequential(layers, input_shape=(None, None, 3))
+    mdl = ktf.models.Sequential(layers, input_shape=(None, None, 3), precision="f32")
     for l in mdl.layers:
         l.set_weights(r.getWeights(l.name))
     y = g["narrow_in"]
@@ -65,12 +65,20 @@ def test_tdnn_modes_vs_oracle(ktf):
     x = rng.standard_normal((3, 37, 20)).astype(np.float32)
     for ctx, sub, pad in [([-2, 0, 2], 1, "SAME"), ([-3, -1, 0, 1], 1, "VALID"), ([0], 3, "SAME"),
                           ([-1, 0, 1], 2, "VALID"), ([-2, -1, 0, 1, 2], 1, "SAME"), ([0, 3], 1, "VALID")]:
-        l = ktf.layers.TDNN(24, context=ctx, subsampling_factor=sub, padding=pad, seed=1)
+        l = ktf.layers.TDNN(24, context=ctx, subsampling_factor=sub, padding=pad, seed=1, precision="f32")
         got = l(x)
         kernel, bias = l.get_weights()
         want = O.tdnn(x, kernel, bias, ctx, sub, pad)
         assert got.shape == want.shape == tuple(l.compute_output_shape(x.shape)), (ctx, sub, pad)
         assert np.max(np.abs(got - want)) < 1e-4, (ctx, sub, pad)
+        # the same modes on the tcgen05 engine (default precision): exact product of the
+        # bf16-rounded operands, fp32 accumulation
+        lt = ktf.layers.TDNN(24, context=ctx, subsampling_factor=sub, padding=pad, seed=1)
+        assert lt.precision is None
+        got_tc = lt(x)
+        want_tc = O.tdnn(_bf16_round(x), _bf16_round(kernel), bias, ctx, sub, pad)
+        assert got_tc.shape == want.shape, (ctx, sub, pad)
+        assert np.max(np.abs(got_tc - want_tc)) < 1e-4, (ctx, sub, pad)
     with pytest.raises(ValueError):
         ktf.layers.TDNN(8, subsampling_factor=0)
     with pytest.raises(ValueError):
@@ -282,7 +290,7 @@ def test_sitw_stack_bf16_vs_oracle(ktf):
 def test_xvector_extractor_bf16_vs_oracle(ktf):
     wav = read_wav_int16(golden_path("librispeech_2.wav"))
     cfg = extractor_cfg()
-    ext = ktf.models.XvectorExtractor(cfg, precision="bf16", seed=0)
+    ext = ktf.models.XvectorExtractor(cfg, precision="bf16", seed=0, allow_random_init=True)
     got = ext(wav)
     want = O.xvector_extractor(wav, cfg, sitw_layers_for_oracle(ext.xvec), ext.xvecGlobalMean, ext.ldaTransform)
     assert cosine(got, want) >= 0.9999, cosine(got, want)
@@ -305,7 +313,7 @@ def test_xvector_extractor_cfg1_vs_oracle(ktf):
     # BASELINE config 1: librispeech_2.wav, batch 1, dither 0, real LDA/mean, random TDNN (seed 0)
     wav = read_wav_int16(golden_path("librispeech_2.wav"))
     cfg = extractor_cfg()
-    ext = ktf.models.XvectorExtractor(cfg, precision="f32", seed=0)
+    ext = ktf.models.XvectorExtractor(cfg, precision="f32", seed=0, allow_random_init=True)
     got, inter = ext(wav, return_intermediate=True)
     assert got.shape == (128,)
     want, ointer = O.xvector_extractor(wav, cfg, sitw_layers_for_oracle(ext.xvec),
@@ -328,7 +336,7 @@ def test_xvector_extractor_cfg1_vs_oracle(ktf):
 def test_xvector_extractor_ragged_batch(ktf):
     wav = read_wav_int16(golden_path("librispeech_2.wav"))
     parts = [wav[:80000], wav[80000:200000], wav[150000:], wav[:48000]]
-    ext = ktf.models.XvectorExtractor(extractor_cfg(), precision="f32", seed=0)
+    ext = ktf.models.XvectorExtractor(extractor_cfg(), precision="f32", seed=0, allow_random_init=True)
     batch = ext(parts)
     assert batch.shape == (4, 128)
     for b, p in enumerate(parts):
@@ -350,14 +358,17 @@ def test_xvector_extractor_from_config(ktf):
     cwd = os.getcwd()
     os.chdir(root)
     try:
+        with pytest.raises(FileNotFoundError):            # final.raw is not vendored: the drop-in call must not
+            ktf.models.XvectorExtractorFromConfig(yml)      # silently return random-weight x-vectors
         with pytest.warns(UserWarning):
-            ext = ktf.models.XvectorExtractorFromConfig(yml, precision="f32")
+            ext = ktf.models.XvectorExtractorFromConfig(yml, precision="f32", allow_random_init=True)
+        assert ext.randomInit
     finally:
         os.chdir(cwd)
     assert ext.mfcc.windowing.dither == 1.0                 # YAML default, like the reference
     wav = read_wav_int16(golden_path("librispeech_2.wav"))
     a = ext(wav)
-    ref = ktf.models.XvectorExtractor(extractor_cfg(), precision="f32", seed=0)(wav)
+    ref = ktf.models.XvectorExtractor(extractor_cfg(), precision="f32", seed=0, allow_random_init=True)(wav)
     # reference's own e2e tolerance with dither on (xvector_extractor_test.py:30)
     assert 1.0 - cosine(a, ref) <= 0.075
 
