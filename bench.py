@@ -1,35 +1,37 @@
 #!/usr/bin/env python
 """
-bench.py -- headline benchmark of the wav -> x-vector hot path (BASELINE.json).
+bench.py -- headline benchmark of the wav -> x-vector hot path (BASELINE.json: "wav2xvec audio-sec/sec at 1/2/4/8
+B200; MFCC GB/s vs HBM peak").
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
-                    [--workload frontend|wav2xvec|tdnn|plda] [--no-stages] [--no-cpu-baseline]
+                    [--workload wav2xvec|frontend|tdnn|plda] [--no-stages] [--no-cpu-baseline]
 
-Default workload (N = 1 and under torchrun): BASELINE config 2, the configuration the metric is quoted
-on -- MFCC(30 mfcc / 30 mel) + CMVN(window 200) on 1024 x 10 s of synthetic 16 kHz audio per GPU
-(float32, +-32767 scale).  One "step" = one pass of the hot path over one batch.  Utterances are sharded,
-there is NO data-path collective ("weak" scaling); value = all ranks' audio seconds / max-over-ranks
-device time.
+Default workload (N = 1 and under torchrun): the BASELINE config 4 shard -- full wav2xvec (fused MFCC -> VAD mask +
+compaction -> CMVN(300) -> SITW TDNN on the tcgen05 stack -> statistics -> LDA / length-norm) on 1024 gated-noise
+utterances x 10 s of synthetic 16 kHz audio per GPU, through models.XvectorExtractor (the reference's
+models/kaldi/xvector_extractor.py:137-186).  One "step" = one pass of the hot path over one batch.  Utterances are
+sharded, there is NO data-path collective ("weak" scaling); value = all ranks' audio seconds / max-over-ranks device time.
 
 One JSON line is printed by rank 0 (DESIGN.md section 6 explains every field):
   value        audio-seconds per second with the batch already resident in HBM (CUDA events)
-  e2e          the same metric through the public layer API with HOST (pinned) buffers: H2D of the audio
-               and D2H of the result are inside the timed region every step
-  roofline     the dominant kernel: algorithmic bytes (or FLOPs) per launch / its own device time vs the
-               measured peak in MEASURED_PEAKS.json
-  cpu_baseline the CPU oracle (oracle/ktf_oracle.py, an op-for-op NumPy port of the reference's layers;
-               the reference itself needs TensorFlow 2.8, not installable here) on a bounded sample
-  stages       (N = 1, default workload only) the other BASELINE configs measured in the same run:
-               TDNN stack (config 3), full wav2xvec shard (config 4), PLDA scoring (config 5)
+  e2e          the same metric through the public model API with HOST (pinned) buffers: H2D of the audio and D2H of the
+               x-vectors are inside the timed region every step; with the achieved H2D rate per rank and the box's
+               measured concurrent pinned-memcpy ceiling beside it
+  roofline     the dominant kernels (the tcgen05 TDNN stack): algorithmic FLOPs per step / their own device time vs the
+               measured bf16 peaks in MEASURED_PEAKS.json (sustained = `frac`, burst = `frac_of_burst`)
+  cpu_baseline the CPU oracle (oracle/ktf_oracle.py, an op-for-op NumPy port of the reference's layers; the reference
+               itself needs TensorFlow 2.8, not installable here) on a bounded sample (N = 1 only)
+  stages       the other BASELINE configs measured in the same run, each with its own roofline:
+                 frontend  config 2, MFCC(30/30) + CMVN(200) on 1024 x 10 s, HBM roofline of the fused kernel
+                 tdnn      config 3, SITW stack on 512 x 300 frames (N = 1 only)
+                 plda      config 5, 50 000 x 50 000 trials, enrolled columns sharded over the N ranks, the all-gather of
+                           the transformed test vectors (NCCL) timed separately, `parity_max_rel` of a sampled
+                           sub-block against the float64 oracle
 
-Other workloads make one of those stages the headline line with the same schema:
-  wav2xvec     full pipeline with VAD + CMVN + TDNN(bf16) + LDA on gated-noise utterances (config 4 shard)
-  tdnn         SITW TDNN stack on 512 x 300 frames (config 3), roofline = tensor pipe
-  plda         all-vs-all PLDA scoring, enrolled columns sharded over the ranks, test vectors exchanged
-               with one NCCL all-gather (config 5); roofline = HBM writes of the fp32 scores
+`--workload X` makes one of the stages the headline line with the same schema.
 
-`--impl reference` times the CPU port with all host threads on a bounded sample of the same workload
-(rank 0 only); it is the only other place allowed to execute oracle/.
+`--impl reference` times the CPU port with all host threads on a bounded sample of the same workload (rank 0 only); it
+is the only other place allowed to execute oracle/.
 """
 
 import argparse
@@ -292,6 +294,7 @@ class CpuPort:
 
 
 CPU_SAMPLE = {"frontend": 192, "wav2xvec": 16, "tdnn": 32, "plda": 768}
+DEFAULT_WORKLOAD = "wav2xvec"        # BASELINE.json metric: wav2xvec audio-sec/sec (config 4 shard per GPU)
 WORKLOAD_UNIT = {"frontend": "audio-s/s", "wav2xvec": "audio-s/s", "tdnn": "audio-s/s", "plda": "scores/s"}
 WORKLOAD_METRIC = {"frontend": "audio_sec_per_sec", "wav2xvec": "audio_sec_per_sec",
                    "tdnn": "audio_sec_per_sec", "plda": "plda_scores_per_sec"}
@@ -327,7 +330,8 @@ def workload_config(workload, n_gpus):
         base.update({"workload": "BASELINE config 4 shard: full wav2xvec (MFCC -> VAD mask -> CMVN(300) -> SITW TDNN "
                                  "bf16 -> stats -> LDA/length-norm), 1024 gated-noise utterances x 10 s per GPU, "
                                  "random-init TDNN (Kaldi weights not vendored), real LDA / mean",
-                     "batch_per_gpu": BATCH, "utt_seconds": UTT_SECONDS, "tdnn_precision": "bf16 operands, fp32 accumulate",
+                     "batch_per_gpu": BATCH, "utt_seconds": UTT_SECONDS, "tdnn_precision": "bf16 operands, fp32 accumulate "
+                     "(the API default)", "host_syncs_per_step": 0,
                      "l2_policy": "655 MB of audio and > 1 GB of activations per step, larger than the 126 MB L2"})
     elif workload == "tdnn":
         base.update({"workload": "BASELINE config 3: SITW x-vector TDNN (5 TDNN-512 + 1500-d stats + 512 embedding, "
@@ -485,18 +489,48 @@ def stage_tdnn(h, steps, warmup):
             "flops": flops, "ms_e2e": ms_e2e, "h2d": B * Tn * 30 * 4, "d2h": B * 512 * 4}
 
 
+def h2d_ceiling(h, mbytes=256, reps=6):
+    """The box's pinned-memcpy H2D rate with ALL ranks copying at once (plain cudaMemcpyAsync loop, no compute): the
+    ceiling any end-to-end number that ships the audio over PCIe can reach.  Returns GB/s (this rank, min over ranks,
+    sum over ranks)."""
+    torch = h.torch
+    host = torch.empty(mbytes << 20, dtype=torch.uint8, pin_memory=True)
+    dev = torch.empty(mbytes << 20, dtype=torch.uint8, device=h.dev)
+    dev.copy_(host, non_blocking=True)
+    h.barrier()
+    a, b = ev_pair(torch)
+    a.record()
+    for _ in range(reps):
+        dev.copy_(host, non_blocking=True)
+    b.record()
+    h.barrier()
+    gbs = reps * (mbytes << 20) / (a.elapsed_time(b) * 1e-3) / 1e9
+    t = torch.tensor([gbs, -gbs, gbs], device=h.dev, dtype=torch.float64)
+    if h.world > 1:
+        mx = t[:2].clone()
+        h.dist.all_reduce(mx, op=h.dist.ReduceOp.MAX)
+        sm = t[2:].clone()
+        h.dist.all_reduce(sm, op=h.dist.ReduceOp.SUM)
+        return gbs, float(-mx[1].item()), float(sm[0].item())
+    return gbs, gbs, gbs
+
+
 def stage_wav2xvec(h, steps, warmup, batch=BATCH):
     import kaldi_tflite_b200 as ktf
     torch = h.torch
-    ext = ktf.models.XvectorExtractor(extractor_cfg(), precision="bf16", seed=0, allow_random_init=True)
+    # default precision of the public API: bf16 operands on the tcgen05 stack
+    ext = ktf.models.XvectorExtractor(extractor_cfg(), seed=0, allow_random_init=True)
     wav = gated_noise_cuda(batch, 7 + h.rank, h.dev)
     _, inter = ext(wav, return_intermediate=True)
-    kept = int(inter["voiced_offsets"][-1].item())
+    kept = int(inter["voiced_offsets"][-1].item())           # outside the timed region: for the FLOP count only
+    assert ext.xvec._stack is not None, "the TDNN stack is not on the tcgen05 engine"
 
     def step(pairs):
         if pairs is None:
             ext(wav)
             return
+        # exactly ext(wav) (models/xvector_extractor.py), with an event pair around the TDNN stack; nothing in it
+        # synchronises with the host (the kept-row count after VAD stays on the device)
         feats, offsets = ext.features(*ext._flatten(wav))
         mask = ext.vad.mask_ragged(feats, offsets)
         voiced, voffs, _ = ext.vad.compact_ragged(feats, mask, offsets, gather=True)
@@ -523,11 +557,30 @@ def stage_wav2xvec(h, steps, warmup, batch=BATCH):
     def e2e_pcm(pairs):
         parallel.stream_batches(ext, host_pcm, 128, host_out)
     ms_e2e_pcm, _, _, _ = h.timed(e2e_pcm, steps, 2)
+    ceil_rank, ceil_min, ceil_sum = h2d_ceiling(h)
     return {"ms": ms, "steps": steps, "launches": launches, "clocks": clocks,
             "pcm16": {"ms_e2e": ms_e2e_pcm, "h2d": batch * UTT_SAMPLES * 2},
             "units": batch * UTT_SECONDS * h.world * steps, "tdnn_ms": tdnn_ms,
             "flops": TDNN_FLOP_PER_FRAME * kept + TDNN_FLOP_PER_UTT * batch, "vad_keep": kept / (batch * FRAMES),
-            "ms_e2e": ms_e2e, "h2d": batch * UTT_SAMPLES * 4, "d2h": batch * 128 * 4}
+            "ms_e2e": ms_e2e, "h2d": batch * UTT_SAMPLES * 4, "d2h": batch * 128 * 4,
+            "h2d_ceiling": {"per_rank_min_gbs": ceil_min, "aggregate_gbs": ceil_sum,
+                            "how": "plain pinned cudaMemcpyAsync loop, 256 MB x 6, all ranks at once"}}
+
+
+def plda_parity(layer, x_test_rows, x_enroll_rows, got_block):
+    """Checker (outside every timed region): a sampled sub-block of the scores against the float64 oracle, evaluated in
+    the reference's direct form.  Returns max |delta| / max(|s|, 1)."""
+    from oracle import ktf_oracle as O
+    worst = 0.0
+    nt, ne = x_test_rows.shape[0], x_enroll_rows.shape[0]
+    for i in range(0, nt, 256):                               # the (B, dim, B) form: keep the temporaries near 1 GB
+        xs = np.concatenate([x_test_rows[i:i + 256], x_enroll_rows]).astype(np.float32)
+        u = O.plda_transform(xs, layer.mean, layer.transformMat, layer.psi, dtype=np.float64)
+        k = xs.shape[0] - ne
+        want = O.plda_llr(u, layer.psi)[:k, k:]
+        got = got_block[i:i + k]
+        worst = max(worst, float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0))))
+    return worst
 
 
 def stage_plda(h, steps, warmup, n=50000):
@@ -543,17 +596,48 @@ def stage_plda(h, steps, warmup, n=50000):
         x = torch.randn((count, PLDA_DIM), generator=g, device=h.dev)
         return x / x.norm(dim=1, keepdim=True) * PLDA_DIM ** 0.5
     x_test, x_enroll = xvecs(hi - lo), xvecs(hi - lo)
-    scores = torch.empty((n, hi - lo), device=h.dev, dtype=torch.float32)
+    scores = torch.empty((n, hi - lo), device=h.dev, dtype=torch.float32)        # this rank's block: 10 GB / G
 
     counts = [parallel.shard_range(n, r, h.world)[1] - parallel.shard_range(n, r, h.world)[0] for r in range(h.world)]
 
     def step(pairs):
         # transforms + the only collective (all-gather of the transformed test vectors as per-rank async
         # broadcasts, 25.6 MB in total) + the score GEMM of every arriving row block
-        parallel.plda_score_sharded(layer, x_test, x_enroll, test_counts=counts)
+        parallel.plda_score_sharded(layer, x_test, x_enroll, test_counts=counts, out=scores)
     ms, launches, clocks, _ = h.timed(step, steps, warmup)
-    # the score kernel alone (roofline): this rank's (n x n/G) block from vectors already gathered
-    u_all = parallel.gather_rows(layer.transformVector(x_test))
+
+    # ---- in-run parity: sampled rows x sampled columns of THIS rank's block against the float64 oracle
+    sc, u_all_chk = parallel.plda_score_sharded(layer, x_test, x_enroll, test_counts=counts, out=scores)
+    rs = np.random.default_rng(5 + h.rank)
+    ti = np.sort(rs.choice(hi - lo, size=min(1024, hi - lo), replace=False))       # local test rows (global = lo + ti)
+    ei = np.sort(rs.choice(hi - lo, size=min(1024, hi - lo), replace=False))
+    tI, eI = torch.from_numpy(ti).to(h.dev), torch.from_numpy(ei).to(h.dev)
+    got_block = sc[lo:hi][tI][:, eI].cpu().numpy()
+    parity = plda_parity(layer, x_test[tI].cpu().numpy(), x_enroll[eI].cpu().numpy(), got_block)
+    parity = h.max_over_ranks(parity)
+
+    # ---- the exchange alone (NCCL all-gather of the transformed test vectors), device-timed
+    u_local = layer.transformVector(x_test)
+
+    def gather_only(pairs):
+        a, b = ev_pair(torch)
+        if pairs is not None:
+            a.record()
+        if h.world > 1:
+            _, _, works = parallel.exchange_test_vectors(u_local, counts)
+            for wk in works:
+                if wk is not None:
+                    wk.wait()
+        if pairs is not None:
+            b.record()
+            pairs.append((a, b))
+    gather_ms = 0.0
+    if h.world > 1:
+        _, _, _, gather_ms = h.timed(gather_only, steps, 2)
+        gather_ms = h.max_over_ranks(gather_ms)
+
+    # ---- the score kernel alone (roofline): this rank's (n x n/G) block from vectors already gathered
+    u_all = parallel.gather_rows(u_local)
     u_enroll = layer.transformVector(x_enroll)
 
     def score_only(pairs):
@@ -570,12 +654,13 @@ def stage_plda(h, steps, warmup, n=50000):
     host_top = torch.empty((n,), dtype=torch.float32, pin_memory=True)
 
     def e2e(pairs):
-        sc, _ = parallel.plda_score_sharded(layer, host_t.to(h.dev, non_blocking=True),
-                                            host_e.to(h.dev, non_blocking=True), test_counts=counts)
-        host_top.copy_(sc.max(dim=1).values, non_blocking=True)        # result read back: best trial per test vector
+        sc2, _ = parallel.plda_score_sharded(layer, host_t.to(h.dev, non_blocking=True),
+                                             host_e.to(h.dev, non_blocking=True), test_counts=counts, out=scores)
+        host_top.copy_(sc2.max(dim=1).values, non_blocking=True)        # result read back: best trial per test vector
     ms_e2e, _, _, _ = h.timed(e2e, steps, 2)
     return {"ms": ms, "steps": steps, "launches": launches, "clocks": clocks, "units": float(n) * n * steps,
             "score_ms": score_ms, "score_bytes": float(n) * (hi - lo) * 4, "flops": 2.0 * n * (hi - lo) * PLDA_DIM,
+            "allgather_ms": gather_ms, "allgather_bytes": n * PLDA_DIM * 4, "parity_max_rel": parity, "n": n,
             "ms_e2e": ms_e2e, "h2d": 2 * (hi - lo) * PLDA_DIM * 4, "d2h": n * 4}
 
 
@@ -634,30 +719,43 @@ def stage_frontend(h, steps, warmup):
             "ms_e2e": ms_e2e, "h2d": BATCH * UTT_SAMPLES * 4, "d2h": BATCH * FRAMES * NUM_CEPS * 4}
 
 
+def measured_traffic(kernel_key):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture (profiles/r02_traffic.json, written
+    by scripts/summarize_profiles.py from the .ncu-rep of the same bench command); None when there is no capture."""
+    tf = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(tf):
+        return None, None
+    with open(tf) as f:
+        d = json.load(f)
+    e = d.get(kernel_key)
+    if not e:
+        return None, None
+    return e.get("dram_bytes_per_launch"), f"profiles/r02_traffic.json ({e.get('source', 'ncu --set full')})"
+
+
 def roofline_for(workload, r, pk):
     if workload == "frontend":
         achieved = ALGO_BYTES_PER_UTT * BATCH / (r["kernel_ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
-                "traffic": None, "peak_source": pk["src"] + " hbm_gbs",
-                "kernel": "frontend_r16_kernel (framing+window+FFT+mel+log+DCT)", "kernel_ms": r["kernel_ms"],
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UTT * BATCH}
-        tf = os.path.join(ROOT, "profiles", "frontend_traffic.json")
-        if os.path.exists(tf):
-            with open(tf) as f:
-                roof["traffic"] = json.load(f).get("dram_bytes_per_launch")
-        return roof
+        traffic, src = measured_traffic("frontend")
+        return {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+                "traffic": traffic, "traffic_source": src, "peak_source": pk["src"] + " hbm_gbs",
+                "kernel": r.get("kernel_name", "frontend kernel (framing+window+FFT+mel+log+DCT)"),
+                "kernel_ms": r["kernel_ms"], "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UTT * BATCH}
     if workload in ("tdnn", "wav2xvec"):
         ms = r["ms"] / r["steps"] if workload == "tdnn" else r["tdnn_ms"]
         flops = r["flops"] / r["steps"] if workload == "tdnn" else r["flops"]
         achieved = flops / (ms * 1e-3) / 1e12
+        traffic, src = measured_traffic("tdnn_stack")
         return {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "frac_of_burst": achieved / pk["tf_burst"], "traffic": None,
-                "peak_source": pk["src"] + " bf16_tflops_sustained (kernels timed inside a long step)",
+                "frac": achieved / pk["tf_sustained"], "peak_burst": pk["tf_burst"],
+                "frac_of_burst": achieved / pk["tf_burst"], "traffic": traffic, "traffic_source": src,
+                "peak_source": pk["src"] + " bf16_tflops_sustained (kernels timed inside a long step); burst beside it",
                 "kernel": "tdnn_tc_kernel x7 (tcgen05 implicit-GEMM stack incl. splice / finalize launches)",
                 "kernel_ms": ms, "algorithmic_flops_per_launch": flops}
     achieved = r["score_bytes"] / (r["score_ms"] * 1e-3) / 1e9
+    traffic, src = measured_traffic("plda_score")
     return {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
-            "traffic": None, "peak_source": pk["src"] + " hbm_gbs",
+            "traffic": traffic, "traffic_source": src, "peak_source": pk["src"] + " hbm_gbs",
             "kernel": "tdnn_tc_kernel<F32> as PLDA score GEMM (fp16 hi/lo split, K = 3*dim) + split / A_i / B_j kernels",
             "kernel_ms": r["score_ms"], "algorithmic_bytes_per_launch": r["score_bytes"],
             "tensor_tflops": r["flops"] * 3 / (r["score_ms"] * 1e-3) / 1e12}
@@ -682,6 +780,25 @@ def pcm16_summary(r, pk, steps):
     return out
 
 
+def stage_summary(name, st, pk):
+    roof = roofline_for(name, st, pk)
+    out = {"value": st["units"] / (st["ms"] * 1e-3), "unit": WORKLOAD_UNIT[name],
+           "ms_per_step": st["ms"] / st["steps"], "launches_per_step": st["launches"] // st["steps"],
+           "e2e_value": st["units"] / (st["ms_e2e"] * 1e-3),
+           "roofline": {k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms", "traffic")}}
+    if "frac_of_burst" in roof:
+        out["roofline"]["frac_of_burst"] = roof["frac_of_burst"]
+    if name == "plda":
+        out.update({"n": st["n"], "allgather_ms": st["allgather_ms"], "allgather_bytes": st["allgather_bytes"],
+                    "score_ms": st["score_ms"], "parity_max_rel": st["parity_max_rel"],
+                    "parity": "sampled 1024 x 1024 sub-block per rank vs the float64 oracle, |d| / max(|s|, 1), max over ranks"})
+    if "vad_keep" in st:
+        out["vad_keep_fraction"] = st["vad_keep"]
+    if "pcm16" in st:
+        out["int16_input"] = pcm16_summary(st, pk, st["steps"])
+    return out
+
+
 def run_ours(args):
     h = Harness(args)
     pk = peaks()
@@ -689,48 +806,53 @@ def run_ours(args):
     r = STAGES[w](h, args.steps, args.warmup)
     line = None
     if h.rank == 0:
+        e2e_s = r["ms_e2e"] * 1e-3 / args.steps
         line = {
             "metric": WORKLOAD_METRIC[w], "value": r["units"] / (r["ms"] * 1e-3), "unit": WORKLOAD_UNIT[w],
             "n_gpus": h.world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": r["ms"] / args.steps, "higher_is_better": True,
             "scaling": "strong" if w == "plda" else "weak",
             "vs_baseline": None, "dtype": {"frontend": "f32", "plda": "f32 (fp16 hi/lo split products, fp32 accumulate)"}.get(
-                w, "bf16 operands, fp32 accumulate"),
+                w, "bf16 operands, fp32 accumulate (front-end f32)"),
             "data": "synthetic", "config": workload_config(w, h.world),
             "roofline": roofline_for(w, r, pk),
             "e2e": {"value": r["units"] / (r["ms_e2e"] * 1e-3), "unit": WORKLOAD_UNIT[w],
-                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["ms_e2e"] / args.steps},
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["ms_e2e"] / args.steps,
+                    "h2d_gbs_per_rank": r["h2d"] / e2e_s / 1e9},
             "gpu_launches": r["launches"], "clocks": r["clocks"],
         }
+        if "h2d_ceiling" in r:
+            line["e2e"]["h2d_ceiling"] = r["h2d_ceiling"]
+            line["e2e"]["h2d_frac_of_ceiling"] = line["e2e"]["h2d_gbs_per_rank"] / r["h2d_ceiling"]["per_rank_min_gbs"]
         if "vad_keep" in r:
             line["config"]["vad_keep_fraction"] = r["vad_keep"]
         if "pcm16" in r:
             line["int16_input"] = pcm16_summary(r, pk, args.steps)
-    # the other configs, measured in the same run (N = 1, default workload only)
-    if w == "frontend" and h.world == 1 and not args.no_stages:
+        if w == "plda":
+            line.update({"allgather_ms": r["allgather_ms"], "parity_max_rel": r["parity_max_rel"]})
+    # the other BASELINE configs, measured in the same run (default workload only).  Every rank runs them (the
+    # PLDA stage is the sharded one: its all-gather needs all ranks); rank 0 reports.
+    if w == DEFAULT_WORKLOAD and not args.no_stages:
         stages = {}
-        for name, kw in (("tdnn", {}), ("wav2xvec", {}), ("plda", {"n": 32768})):
+        plan = [("frontend", {}), ("plda", {"n": 50000})]
+        if h.world == 1:
+            plan.insert(1, ("tdnn", {}))
+        for name, kw in plan:
             try:
-                s = STAGES[name](h, max(3, args.steps // 4), 3, **kw)
-                roof = roofline_for(name, s, pk)
-                stages[name] = {"value": s["units"] / (s["ms"] * 1e-3), "unit": WORKLOAD_UNIT[name],
-                                "ms_per_step": s["ms"] / s["steps"], "launches_per_step": s["launches"] // s["steps"],
-                                "e2e_value": s["units"] / (s["ms_e2e"] * 1e-3),
-                                "roofline": {k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms")}}
-                if name == "plda":
-                    stages[name]["n"] = kw["n"]
-                if "vad_keep" in s:
-                    stages[name]["vad_keep_fraction"] = s["vad_keep"]
-                if "pcm16" in s:
-                    stages[name]["int16_input"] = pcm16_summary(s, pk, s["steps"])
+                st = STAGES[name](h, max(3, args.steps // 4), 3, **kw)
+                stages[name] = stage_summary(name, st, pk)
             except Exception as e:                              # a stage must never take the headline line down
                 stages[name] = {"error": f"{type(e).__name__}: {e}"}
-        line["stages"] = stages
+                if h.world > 1:
+                    raise                                       # ... but ranks must not diverge inside a collective
+        if h.rank == 0:
+            line["stages"] = stages
     if h.rank == 0:
         if h.world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, 1)           # bounded sample, 1 thread, rank 0, N = 1 only
         emit_json(line)
     if h.world > 1:
+        h.dist.barrier()
         h.dist.destroy_process_group()
 
 
@@ -762,7 +884,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="frontend", choices=sorted(STAGES))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(STAGES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
     args = ap.parse_args()

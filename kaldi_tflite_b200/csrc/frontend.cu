@@ -90,7 +90,10 @@ struct Geo {
   static constexpr int NSLOT = R / 8;      // k1 columns a lane owns after the transpose
   static constexpr int RS = R + 2;         // complex row stride of the transpose tile / twiddle table
   static constexpr int TFS = ((8 * RS * 2 + 31) / 32) * 32 + 16;  // floats per frame tile (== 16 mod 32)
-  static constexpr int QS = C + 8;         // floats per frame of the power buffer (== 8 mod 32)
+  // floats per frame of the power buffer.  The chunk swizzle of qidx() sends the Nyquist chunk C/4 to C/4 ^ ((C/32) & 7):
+  // itself for C = 256, but chunk 36 for C = 128 -- the 256-point FFT needs 16 more floats per frame (without them the
+  // Nyquist power of frame f landed on bins 8..11 of frame f + 1)
+  static constexpr int QS = C + (R == 16 ? 24 : 8);
 };
 
 // Power-buffer index of bin k: 4-bin chunks are XOR-swizzled so that the eight lanes of a frame,

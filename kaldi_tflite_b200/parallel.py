@@ -48,22 +48,13 @@ def gather_rows(local, counts=None):
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
 
 
-def plda_score_sharded(plda, x_test_local, x_enroll_local, test_counts=None):
+def exchange_test_vectors(u_test_local, test_counts=None):
     """
-    Sharded PLDA trial scoring.  Each rank holds a slice of the test x-vectors and a slice of the enrolled
-    x-vectors (raw, (n, dim) float32).  Returns this rank's block scores[all tests, local enrolled] -- test
-    rows ordered by rank -- plus the gathered transformed test vectors.
-
-    The exchange is an all-gather of the transformed test vectors, issued as one asynchronous broadcast per
-    source rank so that the score GEMM of rank r's row block starts as soon as ITS vectors have arrived and
-    the remaining transfers overlap the tensor-core work.  `test_counts` (rows per rank) saves
-    the small size exchange when the caller already knows the partition (e.g. from `shard_range`).
+    The one collective of the PLDA path: all-gather of the transformed test vectors, issued as one
+    asynchronous broadcast per source rank so that consumers can start on block r as soon as IT has arrived.
+    Returns (u_all, offsets, works): `works[r].wait()` makes the current stream wait for rank r's block only.
     """
     rank, w = world()
-    u_test_local = plda.transformVector(x_test_local.contiguous())
-    u_enroll_local = plda.transformVector(x_enroll_local.contiguous())
-    if w == 1:
-        return plda.logLikelihoodRatio(u_test_local, u_enroll_local), u_test_local
     if test_counts is None:
         n = torch.tensor([u_test_local.shape[0]], device=u_test_local.device, dtype=torch.int64)
         sizes = [torch.zeros_like(n) for _ in range(w)]
@@ -76,7 +67,28 @@ def plda_score_sharded(plda, x_test_local, x_enroll_local, test_counts=None):
     u_all[offs[rank]:offs[rank + 1]].copy_(u_test_local)
     works = [dist.broadcast(u_all[offs[r]:offs[r + 1]], src=r, async_op=True) if offs[r + 1] > offs[r] else None
              for r in range(w)]
-    scores = torch.empty((offs[-1], u_enroll_local.shape[0]), device=u_test_local.device, dtype=u_test_local.dtype)
+    return u_all, offs, works
+
+
+def plda_score_sharded(plda, x_test_local, x_enroll_local, test_counts=None, out=None):
+    """
+    Sharded PLDA trial scoring.  Each rank holds a slice of the test x-vectors and a slice of the enrolled
+    x-vectors (raw, (n, dim) float32).  Returns this rank's block scores[all tests, local enrolled] -- test
+    rows ordered by rank -- plus the gathered transformed test vectors.
+
+    The exchange is an all-gather of the transformed test vectors (`exchange_test_vectors`): the score GEMM of rank
+    r's row block starts as soon as ITS vectors have arrived and the remaining transfers overlap the tensor-core work
+    (SURVEY.md 8e).  `test_counts` (rows per rank) saves the small size exchange when the caller already knows the
+    partition (e.g. from `shard_range`); `out` is an optional preallocated (n_test, n_enroll_local) score block.
+    """
+    rank, w = world()
+    u_test_local = plda.transformVector(x_test_local.contiguous())
+    u_enroll_local = plda.transformVector(x_enroll_local.contiguous())
+    if w == 1:
+        return plda.logLikelihoodRatio(u_test_local, u_enroll_local, out=out), u_test_local
+    u_all, offs, works = exchange_test_vectors(u_test_local, test_counts)
+    scores = out if out is not None else torch.empty((offs[-1], u_enroll_local.shape[0]), device=u_test_local.device,
+                                                     dtype=u_test_local.dtype)
     for r in range(w):
         if works[r] is None:
             continue
