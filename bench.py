@@ -293,7 +293,7 @@ class CpuPort:
         return time.perf_counter() - t0, float(n) * n, "scores"
 
 
-CPU_SAMPLE = {"frontend": 192, "wav2xvec": 16, "tdnn": 32, "plda": 768}
+CPU_SAMPLE = {"frontend": 192, "wav2xvec": 384, "tdnn": 32, "plda": 768}
 DEFAULT_WORKLOAD = "wav2xvec"        # BASELINE.json metric: wav2xvec audio-sec/sec (config 4 shard per GPU)
 WORKLOAD_UNIT = {"frontend": "audio-s/s", "wav2xvec": "audio-s/s", "tdnn": "audio-s/s", "plda": "scores/s"}
 WORKLOAD_METRIC = {"frontend": "audio_sec_per_sec", "wav2xvec": "audio_sec_per_sec",
@@ -302,7 +302,7 @@ WORKLOAD_METRIC = {"frontend": "audio_sec_per_sec", "wav2xvec": "audio_sec_per_s
 
 def cpu_baseline(workload, threads):
     port = CpuPort()
-    n = CPU_SAMPLE[workload] * (max(1, threads // 2) if workload != "plda" else 1)
+    n = CPU_SAMPLE[workload] * (max(1, threads // 2) if workload != "plda" else 1)     # about 10-20 s of CPU work
     try:
         from threadpoolctl import threadpool_limits
         ctx = threadpool_limits(limits=1 if threads == 1 else None)
@@ -360,8 +360,10 @@ def run_reference(args):
     port = CpuPort()
     w = args.workload
     n = CPU_SAMPLE[w] * (max(1, threads // 2) if w != "plda" else 1)
-    if w != "frontend":
-        n = max(n // 4, threads if w != "plda" else 256)      # keep K + W steps within a few minutes
+    if w == "wav2xvec":
+        n = 64 * threads                                      # about 2 s per step: K + W steps within a few minutes
+    elif w != "frontend":
+        n = max(n // 4, threads if w != "plda" else 256)
     for _ in range(args.warmup):
         getattr(port, w)(n, threads)
     t, units = 0.0, 0.0

@@ -97,7 +97,7 @@ def plda_score_sharded(plda, x_test_local, x_enroll_local, test_counts=None, out
     return scores, u_all
 
 
-def stream_batches(fn, host_in, chunk, host_out=None):
+def stream_batches(fn, host_in, chunk, host_out=None, depth=3):
     """
     Runs `fn` (any layer / model call taking a CUDA tensor of utterances and returning a CUDA tensor with
     the same leading dimension) over a HOST batch in chunks of `chunk` utterances, with the host->device
@@ -105,6 +105,11 @@ def stream_batches(fn, host_in, chunk, host_out=None):
     (two side streams; PCIe is full duplex).  Utterances are independent on this path, so the result equals
     the one-shot call.  `host_in` should be pinned for the copies to be asynchronous; `host_out`, if given,
     is a pinned tensor that receives the results, otherwise the device results are concatenated.
+
+    The audio lands in a ring of `depth` device staging buffers that is allocated once per (chunk shape, dtype) and
+    reused: a slot is refilled only after the compute stream has finished the chunk that used it (event wait on the
+    copy stream -- the HOST never blocks).  Nothing on this path synchronises with the host any more, so without the
+    ring the host would run ahead and ask the allocator for a fresh 80 MB block per chunk.
     """
     dev = T.device()
     cur = torch.cuda.current_stream(dev)
@@ -113,21 +118,32 @@ def stream_batches(fn, host_in, chunk, host_out=None):
     s_out.wait_stream(cur)
     outs = []
     n = host_in.shape[0]
+    ring = _staging_ring(dev, (min(chunk, max(n, 1)),) + tuple(host_in.shape[1:]), host_in.dtype, depth)
+    freed = [None] * depth                       # event: the compute stream is done with slot k
 
-    def fetch(i):
+    def fetch(idx):
+        i = idx * chunk
+        m = min(chunk, n - i)
+        k = idx % depth
+        if freed[k] is not None:
+            s_in.wait_event(freed[k])
         with torch.cuda.stream(s_in):
-            x = host_in[i:i + chunk].to(dev, non_blocking=True)
+            x = ring[k][:m]
+            x.copy_(host_in[i:i + m], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(s_in)
-        return x, ev
+        return x, ev, k
 
+    n_chunks = (n + chunk - 1) // chunk
     nxt = fetch(0) if n > 0 else None
-    for i in range(0, n, chunk):
-        x, ev = nxt
-        nxt = fetch(i + chunk) if i + chunk < n else None    # the next copy is in flight before this chunk computes
+    for idx in range(n_chunks):
+        x, ev, k = nxt
+        nxt = fetch(idx + 1) if idx + 1 < n_chunks else None   # the next copy is in flight before this chunk computes
         cur.wait_event(ev)
-        x.record_stream(cur)
         y = fn(x)
+        freed[k] = torch.cuda.Event()
+        freed[k].record(cur)
+        i = idx * chunk
         if host_out is None:
             outs.append(y)
         else:
@@ -136,10 +152,12 @@ def stream_batches(fn, host_in, chunk, host_out=None):
                 host_out[i:i + y.shape[0]].copy_(y, non_blocking=True)
             y.record_stream(s_out)
     cur.wait_stream(s_out)
+    s_in.wait_stream(cur)                        # the ring may be refilled by the next call only after this one's compute
     return host_out if host_out is not None else torch.cat(outs, dim=0)
 
 
 _SIDE = {}
+_RINGS = {}
 
 
 def _side_streams(dev):
@@ -147,3 +165,12 @@ def _side_streams(dev):
     if key not in _SIDE:
         _SIDE[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
     return _SIDE[key]
+
+
+def _staging_ring(dev, shape, dtype, depth):
+    key = (dev.type, dev.index, tuple(shape), dtype, depth)
+    if key not in _RINGS:
+        if len(_RINGS) >= 4:                      # a handful of shapes per process; drop the oldest
+            _RINGS.pop(next(iter(_RINGS)))
+        _RINGS[key] = [torch.empty(shape, device=dev, dtype=dtype) for _ in range(depth)]
+    return _RINGS[key]

@@ -139,7 +139,13 @@ def test_callhome_frontend_vs_oracle(ktf):
     feats = ktf.layers.MFCC(**CALLHOME_MFCC)(ktf.layers.Framing(25.0, 10.0, 8000.0, dynamic_input_shape=True)(wav))
     vkw = dict(energy_mean_scale=0.5, energy_threshold=5.5, frames_context=2, proportion_threshold=0.12)
     assert np.array_equal(ktf.layers.VAD(return_indexes=False, **vkw)(feats), O.vad(feats, return_indexes=False, **vkw))
-    assert rmse(O.cmvn(feats, window=300), ktf.layers.CMVN(window=300)(feats)) < 1e-5
+    # against the float64 evaluation of the same windows: the float32 oracle carries the rounding of a 1498-frame
+    # float32 cumsum (cmvn.py:172), which alone is ~1e-5 on features of magnitude 20
+    from test_gpu_frontend import _cmvn_f64
+    truth = _cmvn_f64(feats, 300, False, "SAME")
+    got = ktf.layers.CMVN(window=300)(feats)
+    assert rmse(truth, got) < 1e-5
+    assert rmse(truth, got) <= 1.5 * rmse(truth, O.cmvn(feats, window=300))
 
 
 @pytest.mark.parametrize("precision,bar", [("f32", 0.99999), (None, 0.9999)])
