@@ -46,6 +46,43 @@ int ktf_device_arch(void);
 int64_t ktf_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
+ * Context: one per (process, device) for hosts that do not bring their own CUDA runtime binding.  It owns
+ * a non-blocking stream (pass ktf_ctx_stream(ctx) as the `stream` of any entry point below), gives such hosts device
+ * memory and copies, and carries the NCCL communicator of the one collective this path has.  The Python host does not
+ * need it: torch supplies the device memory, the streams and the process group.  Contexts are independent of each other;
+ * one context serves one host thread at a time.
+ * ---------------------------------------------------------------------------------- */
+typedef struct ktf_ctx ktf_ctx;
+int ktf_ctx_create(int32_t device, ktf_ctx** out);
+void ktf_ctx_destroy(ktf_ctx* ctx);
+int32_t ktf_ctx_device(const ktf_ctx* ctx);
+void* ktf_ctx_stream(const ktf_ctx* ctx);            /* cudaStream_t */
+int ktf_ctx_synchronize(ktf_ctx* ctx);               /* waits for the context's stream */
+int ktf_ctx_malloc(ktf_ctx* ctx, int64_t bytes, void** dev_out);
+int ktf_ctx_free(ktf_ctx* ctx, void* dev);
+/* asynchronous on the context's stream */
+int ktf_ctx_memcpy_h2d(ktf_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
+/* enqueued on the context's stream; returns when the host buffer is valid */
+int ktf_ctx_memcpy_d2h(ktf_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+
+/* The only collective of the hot path: PLDA all-vs-all scoring shards the ENROLLED vectors over the GPUs
+ * and all-gathers the transformed TEST vectors, after which every rank scores its own (n_test x n_enroll / G) block with
+ * ktf_plda_score -- layers/plda/plda.py:247-263 scores one set against itself on one device.  NCCL is bound at run time
+ * (libnccl.so.2, or the path in $KTF_NCCL_LIB); ktf_nccl_available() says whether it could be.
+ *   rank 0: ktf_nccl_unique_id(id)  ->  the host ships the KTF_NCCL_UNIQUE_ID_BYTES bytes to every rank (file, socket, MPI)
+ *   every rank: ktf_nccl_comm_init(ctx, nranks, rank, id)   (collective: all ranks must call it)
+ *   ktf_nccl_allgather_xvec: recv_dev[(r * rows_per_rank + i) * dim + d] = rank r's send_dev[i * dim + d]; every rank
+ *   contributes rows_per_rank rows (pad the last shard), elem_bytes = 4 (float32) or 8 (float64) per element.
+ *   stream NULL = the context's stream.  A context without a communicator is a world of one rank (the gather is a copy). */
+#define KTF_NCCL_UNIQUE_ID_BYTES 128
+int ktf_nccl_available(void);
+int ktf_nccl_unique_id(void* id_out_host);
+int ktf_nccl_comm_init(ktf_ctx* ctx, int32_t nranks, int32_t rank, const void* id_host);
+int ktf_nccl_comm_destroy(ktf_ctx* ctx);
+int ktf_nccl_allgather_xvec(ktf_ctx* ctx, const void* send_dev, void* recv_dev, int64_t rows_per_rank, int32_t dim,
+                            int32_t elem_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Front-end: Framing + Windowing + FilterBank + DCT/MFCC in ONE fused kernel.
  * Replaces layers/dsp/framing.py:243-265, windowing.py:180-209, filterbank.py:225-242,
  * dct.py:175-176 and mfcc.py:197-244.  Frames are never materialised in HBM.
@@ -70,7 +107,15 @@ typedef struct {
   float preemphasis;        /* windowing.py:195-200; <= 0 disables */
   float energy_floor;       /* lower clip of the LOG energy (windowing.py:177) */
   float epsilon;            /* added before log (windowing.py:176, filterbank.py:240) */
+  float dither;             /* windowing.py:182-183: every FRAMED sample gets its own dither * N(0,1) (frames that overlap
+                               do not share noise), drawn inside the kernel from a counter-based generator
+                               (Philox4x32-7 keyed by the seed below, counter = (frame, sample); Box-Muller).  Random by
+                               construction: statistically matched to the reference, never bit-matched; 0 disables */
 } ktf_frontend_cfg;
+
+/* Seed of the dither generator (process-wide): forward call number n after this call draws from stream seed + n, so two
+ * runs that set the same seed and issue the same calls produce the same features.  Default seed 0. */
+int ktf_set_dither_seed(uint64_t seed);
 
 typedef struct ktf_frontend ktf_frontend;
 
@@ -304,6 +349,15 @@ int ktf_plda_transform(const ktf_plda* p, const float* x_dev, int64_t n, void* u
 int ktf_plda_score(const ktf_plda* p, const void* u_test_dev, int64_t n_test,
                    const void* u_enroll_dev, int64_t n_enroll, void* scores_dev, int64_t ld,
                    void* stream);
+
+/* Compact score output: at dim 128 the score matrix is bound by its own HBM write (4 bytes per
+ * trial, 64 FLOP per byte), so callers that rank or threshold trials can take the scores as bfloat16 (2 bytes per trial,
+ * relative rounding 2^-9): the fp32-equivalent value A_i + B_j + u_i^T diag(c) u_j is formed in TMEM / registers exactly
+ * as for KTF_SCORES_NATIVE and rounded once on the way out.  KTF_SCORES_BF16 needs a float32 handle; scores_dev is then
+ * (n_test, ld) bfloat16.  KTF_SCORES_NATIVE == ktf_plda_score (plda.py:215-245). */
+enum { KTF_SCORES_NATIVE = 0, KTF_SCORES_BF16 = 1 };
+int ktf_plda_score_ex(const ktf_plda* p, const void* u_test_dev, int64_t n_test, const void* u_enroll_dev,
+                      int64_t n_enroll, void* scores_dev, int64_t ld, int32_t score_format, void* stream);
 
 #ifdef __cplusplus
 }

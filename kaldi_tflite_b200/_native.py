@@ -17,7 +17,9 @@ KTF_OUT_MFCC, KTF_OUT_FBANK, KTF_OUT_WINDOWED = 0, 1, 2
 KTF_SAMPLE_F32, KTF_SAMPLE_S16 = 0, 1
 KTF_PREC_F32, KTF_PREC_BF16 = 0, 1
 KTF_ACT_NONE, KTF_ACT_RELU = 0, 1
+KTF_SCORES_NATIVE, KTF_SCORES_BF16 = 0, 1
 KTF_MAX_CONTEXT = 16
+KTF_NCCL_UNIQUE_ID_BYTES = 128
 KTF_EINVAL, KTF_ECUDA, KTF_ENOMEM = -1, -2, -3
 
 
@@ -30,7 +32,7 @@ class FrontendCfg(Structure):
                 ("num_mels", c_int32), ("num_ceps", c_int32), ("output", c_int32),
                 ("remove_dc_offset", c_int32), ("raw_energy", c_int32), ("use_energy", c_int32),
                 ("use_power", c_int32), ("use_log_fbank", c_int32), ("apply_lifter", c_int32),
-                ("preemphasis", c_float), ("energy_floor", c_float), ("epsilon", c_float)]
+                ("preemphasis", c_float), ("energy_floor", c_float), ("epsilon", c_float), ("dither", c_float)]
 
 
 class VadCfg(Structure):
@@ -51,6 +53,21 @@ _SIGNATURES = {
     "ktf_version": (c_int32, []),
     "ktf_device_arch": (c_int32, []),
     "ktf_launch_count": (c_int64, []),
+    "ktf_set_dither_seed": (c_int32, [ctypes.c_uint64]),
+    "ktf_ctx_create": (c_int32, [c_int32, POINTER(_P)]),
+    "ktf_ctx_destroy": (None, [_P]),
+    "ktf_ctx_device": (c_int32, [_P]),
+    "ktf_ctx_stream": (_P, [_P]),
+    "ktf_ctx_synchronize": (c_int32, [_P]),
+    "ktf_ctx_malloc": (c_int32, [_P, c_int64, POINTER(_P)]),
+    "ktf_ctx_free": (c_int32, [_P, _P]),
+    "ktf_ctx_memcpy_h2d": (c_int32, [_P, _P, _P, c_int64]),
+    "ktf_ctx_memcpy_d2h": (c_int32, [_P, _P, _P, c_int64]),
+    "ktf_nccl_available": (c_int32, []),
+    "ktf_nccl_unique_id": (c_int32, [_P]),
+    "ktf_nccl_comm_init": (c_int32, [_P, c_int32, c_int32, _P]),
+    "ktf_nccl_comm_destroy": (c_int32, [_P]),
+    "ktf_nccl_allgather_xvec": (c_int32, [_P, _P, _P, c_int64, c_int32, c_int32, _P]),
     "ktf_frontend_create": (c_int32, [POINTER(FrontendCfg), _P, _P, _P, _P, POINTER(_P)]),
     "ktf_frontend_destroy": (None, [_P]),
     "ktf_frontend_num_frames": (c_int64, [_P, c_int64]),
@@ -85,6 +102,7 @@ _SIGNATURES = {
     "ktf_plda_destroy": (None, [_P]),
     "ktf_plda_transform": (c_int32, [_P, _P, c_int64, _P, _P]),
     "ktf_plda_score": (c_int32, [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P]),
+    "ktf_plda_score_ex": (c_int32, [_P, _P, c_int64, _P, c_int64, _P, c_int64, c_int32, _P]),
 }
 
 _lib = None

@@ -65,7 +65,7 @@ def build(force=False, verbose=False):
             if log:
                 print(log)
     objs = [o for o, _ in results]
-    cmd = [NVCC] + ARCH_FLAGS + ["-shared", "-o", out] + objs
+    cmd = [NVCC] + ARCH_FLAGS + ["-shared", "-o", out] + objs + ["-ldl"]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"link failed:\n{p.stdout}")

@@ -8,6 +8,7 @@ namespace ktf {
 
 static thread_local char g_err[1024] = "";
 static std::atomic<int64_t> g_launches{0};
+static std::atomic<uint64_t> g_dither_stream{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -18,13 +19,20 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+uint64_t next_dither_stream() { return g_dither_stream.fetch_add(1, std::memory_order_relaxed); }
+
 }  // namespace ktf
 
 extern "C" {
 
 const char* ktf_last_error(void) { return ktf::g_err; }
 
-int ktf_version(void) { return 100; }
+int ktf_version(void) { return 101; }
+
+int ktf_set_dither_seed(uint64_t seed) {
+  ktf::g_dither_stream.store(seed, std::memory_order_relaxed);
+  return KTF_OK;
+}
 
 int ktf_device_arch(void) {
   int dev = 0, major = 0, minor = 0;

@@ -12,6 +12,7 @@ namespace ktf {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+uint64_t next_dither_stream();   // seed + number of dithered forward calls so far (ktf_set_dither_seed)
 
 #define KTF_CHECK_ARG(cond, ...)            \
   do {                                      \

@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendArg
     // ---- windowing (windowing.py:180-209) ------------------------------------------------
     const float* fr = s_span + f * a.shift;
     const bool fvalid = f < cur.nvalid;
+    const bool dithered = a.dither != 0.0f;                       // warp-uniform
+    const long long gframe = cur.out_row0 + cur.frame0 + f;      // global frame index: the dither counter
     float2 z[R];
     float sum = 0.0f;
     if constexpr (MV > 0) {
@@ -188,6 +190,11 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendArg
       for (int m = 0; m < R; ++m) {
         if (m < MV) {
           z[m] = *reinterpret_cast<const float2*>(fr + 2 * (j + 8 * m));
+          if (dithered) {                                         // windowing.py:182-183
+            const float2 nz = dither_pair(a.dither_seed, gframe, j + 8 * m);
+            z[m].x = fmaf(a.dither, nz.x, z[m].x);
+            z[m].y = fmaf(a.dither, nz.y, z[m].y);
+          }
           sum += z[m].x + z[m].y;
         } else {
           z[m] = make_float2(0.0f, 0.0f);
@@ -201,6 +208,11 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendArg
         if (i0 < a.W) {
           x0 = fr[i0];
           if (i0 + 1 < a.W) x1 = fr[i0 + 1];
+          if (dithered) {                                         // windowing.py:182-183
+            const float2 nz = dither_pair(a.dither_seed, gframe, j + 8 * m);
+            x0 = fmaf(a.dither, nz.x, x0);
+            if (i0 + 1 < a.W) x1 = fmaf(a.dither, nz.y, x1);
+          }
         }
         z[m] = make_float2(x0, x1);
         sum += x0 + x1;
@@ -216,7 +228,13 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendArg
         const int i0 = 2 * (j + 8 * m);
         const float x0 = z[m].x - mean, x1 = z[m].y - mean;
         float xm1;
-        if (m == 0) xm1 = j0 ? x0 : fr[i0 - 1] - mean; else xm1 = fr[i0 - 1] - mean;
+        if (m == 0 && j0) {
+          xm1 = x0;
+        } else {
+          float prev = fr[i0 - 1];          // the neighbour lane's sample: its dither is recomputed, not exchanged
+          if (dithered) prev = fmaf(a.dither, dither_pair(a.dither_seed, gframe, j + 8 * m - 1).y, prev);
+          xm1 = prev - mean;
+        }
         const float2 w = *reinterpret_cast<const float2*>(s_window + i0);
         if (a.raw_energy) esum = fmaf(x0, x0, fmaf(x1, x1, esum));
         const float y0 = (x0 - pc * xm1) * w.x;
@@ -233,7 +251,12 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendArg
           const float x0 = z[m].x - mean;
           const bool has1 = (i0 + 1 < a.W);
           const float x1 = has1 ? z[m].y - mean : 0.0f;
-          const float xm1 = (i0 > 0) ? fr[i0 - 1] - mean : x0;
+          float xm1 = x0;
+          if (i0 > 0) {
+            float prev = fr[i0 - 1];
+            if (dithered) prev = fmaf(a.dither, dither_pair(a.dither_seed, gframe, j + 8 * m - 1).y, prev);
+            xm1 = prev - mean;
+          }
           if (a.raw_energy) esum = fmaf(x0, x0, fmaf(x1, x1, esum));
           y0 = (x0 - pc * xm1) * s_window[i0];
           y1 = has1 ? (x1 - pc * x0) * s_window[i0 + 1] : 0.0f;
@@ -526,6 +549,8 @@ void fill_args(const ktf_frontend* fe, FrontendArgs& a) {
   a.preemph = c.preemphasis;
   a.energy_floor = c.energy_floor;
   a.eps = c.epsilon;
+  a.dither = c.dither;
+  a.dither_seed = c.dither != 0.0f ? 0x9E3779B97F4A7C15ull * (ktf::next_dither_stream() + 1) : 0ull;
   a.r16_blob = fe->d_r16;
   a.r16_blob_floats = fe->r16_blob_floats;
   a.r16_nf = fe->r16_nf;
@@ -622,7 +647,7 @@ int ktf_frontend_create(const ktf_frontend_cfg* cfg, const float* window_host,
     if ((rc = ktf::upload(&fe->d_dct, dp.data(), dp.size())) != KTF_OK) return fail(rc);
     if ((rc = ktf::upload(&fe->d_lifter, lf.data(), lf.size())) != KTF_OK) return fail(rc);
   }
-  if (getenv("KTF_FRONTEND_GENERIC") == nullptr &&
+  if (getenv("KTF_FRONTEND_GENERIC") == nullptr && cfg->dither == 0.0f &&   // dither: generic kernel (it draws the noise)
       (rc = r16_build(fe, window_host, mel_bank_host, dct_host, lifter_host)) != KTF_OK) return fail(rc);
   fe->smem_bytes = (R == 32) ? smem_for<32>(fe) : smem_for<16>(fe);
   if (fe->smem_bytes > 227 * 1024) {

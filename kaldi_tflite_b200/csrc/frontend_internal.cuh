@@ -44,6 +44,8 @@ struct FrontendArgs {
   int W, shift, span, M, Kc, out_dim, output, mel_w_len;
   int remove_dc, raw_energy, use_energy, use_power, use_log, apply_lifter;
   float preemph, energy_floor, eps;
+  float dither;                    // windowing.py:182-183; 0 = off (generic kernel only: the fast path is built without it)
+  unsigned long long dither_seed;  // Philox key of this forward call
   // 16 x 16 fast path (frontend_r16.cu): one blob laid out like the CTA's table region
   const float* r16_blob;
   int r16_blob_floats, r16_nf, r16_melw_floats;
@@ -64,6 +66,32 @@ __device__ __forceinline__ void cp_async16(unsigned dst_smem, const float* src) 
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Counter-based noise for the dither of windowing.py:182-183: Philox4x32 (7 rounds: the fewest that pass BigCrush in
+// the Random123 paper) keyed by the call's seed, counter = (global frame index, sample-pair index) -- every FRAMED sample
+// has its own draw, so overlapping frames do not share noise, and a neighbour's draw can be recomputed instead of
+// exchanged.  Returns two N(0,1) values (Box-Muller on the first two outputs; fast intrinsics are ample for dither).
+__device__ __forceinline__ float2 dither_pair(unsigned long long seed, long long frame, int pair) {
+  unsigned c0 = (unsigned)frame, c1 = (unsigned)((unsigned long long)frame >> 32), c2 = (unsigned)pair, c3 = 0x6b746621u;
+  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u1 = ((float)(c0 >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0, 1]
+  const float u2 = (float)(c1 >> 8) * (1.0f / 16777216.0f);            // [0, 1)
+  const float rad = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307179586f * u2, &sn, &cs);
+  return make_float2(rad * cs, rad * sn);
 }
 
 struct Item {

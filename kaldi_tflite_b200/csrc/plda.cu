@@ -139,8 +139,8 @@ __global__ void plda_split_kernel(const float* __restrict__ u, long long n, int 
   }
 }
 
-int score_tc(const ktf_plda* p, const float* ut, int64_t nt, const float* ue, int64_t ne, float* scores, int64_t ld,
-             cudaStream_t st) {
+int score_tc(const ktf_plda* p, const float* ut, int64_t nt, const float* ue, int64_t ne, void* scores, int64_t ld,
+             int scores_bf16, cudaStream_t st) {
   const int dim = p->dim;
   const long long K = 3LL * dim;
   ktf::Carver cv;
@@ -167,7 +167,7 @@ int score_tc(const ktf_plda* p, const float* ut, int64_t nt, const float* ue, in
   KTF_LAUNCH_OK();
   plda_split_kernel<<<blocks(ne * dim), 256, 0, st>>>(ue, ne, dim, nullptr, 1, Bs);
   KTF_LAUNCH_OK();
-  return ktf::tc_gemm_nt(As, nt, K, Bs, ne, K, K, /*fp16=*/1, Ai, Bj, scores, ld, st);
+  return ktf::tc_gemm_nt(As, nt, K, Bs, ne, K, K, /*fp16=*/1, Ai, Bj, scores, ld, scores_bf16, st);
 }
 
 template <typename T>
@@ -304,6 +304,20 @@ int ktf_plda_transform(const ktf_plda* p, const float* x_dev, int64_t n, void* u
                              : transform_impl<double>(p, x_dev, n, (double*)u_dev, st);
 }
 
+int ktf_plda_score_ex(const ktf_plda* p, const void* u_test_dev, int64_t n_test, const void* u_enroll_dev,
+                      int64_t n_enroll, void* scores_dev, int64_t ld, int32_t score_format, void* stream) {
+  KTF_CHECK_ARG(p && u_test_dev && u_enroll_dev && scores_dev, "ktf_plda_score: null argument");
+  KTF_CHECK_ARG(ld >= n_enroll, "ld must be >= n_enroll");
+  KTF_CHECK_ARG(score_format == KTF_SCORES_NATIVE || score_format == KTF_SCORES_BF16, "bad score_format");
+  if (score_format == KTF_SCORES_BF16) {
+    KTF_CHECK_ARG(p->use_tc, "KTF_SCORES_BF16 needs a float32 handle (the tcgen05 score GEMM)");
+    if (n_test <= 0 || n_enroll <= 0) return KTF_OK;
+    return score_tc(p, (const float*)u_test_dev, n_test, (const float*)u_enroll_dev, n_enroll, scores_dev, ld, 1,
+                    (cudaStream_t)stream);
+  }
+  return ktf_plda_score(p, u_test_dev, n_test, u_enroll_dev, n_enroll, scores_dev, ld, stream);
+}
+
 int ktf_plda_score(const ktf_plda* p, const void* u_test_dev, int64_t n_test, const void* u_enroll_dev,
                    int64_t n_enroll, void* scores_dev, int64_t ld, void* stream) {
   KTF_CHECK_ARG(p && u_test_dev && u_enroll_dev && scores_dev, "ktf_plda_score: null argument");
@@ -311,8 +325,7 @@ int ktf_plda_score(const ktf_plda* p, const void* u_test_dev, int64_t n_test, co
   if (n_test <= 0 || n_enroll <= 0) return KTF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (p->use_tc)
-    return score_tc(p, (const float*)u_test_dev, n_test, (const float*)u_enroll_dev, n_enroll, (float*)scores_dev, ld,
-                    st);
+    return score_tc(p, (const float*)u_test_dev, n_test, (const float*)u_enroll_dev, n_enroll, scores_dev, ld, 0, st);
   return p->dtype_bytes == 4
              ? score_impl<float>(p, (const float*)u_test_dev, n_test, (const float*)u_enroll_dev, n_enroll,
                                  (float*)scores_dev, ld, st)

@@ -22,7 +22,9 @@ int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in
 int stats_sums_f32(const float* y_dev, const int64_t* offsets_dev, int64_t batch, int dim, float* sums_dev,
                    cudaStream_t st);
 // tcgen05 engine as a plain "NT" GEMM: C[i, j] = sum_k A[i, k] * B[j, k] + row_add[i] + col_add[j];
-// A (m, K), B (n, K) row-major 16-bit (bf16, or fp16 when fp16 != 0), C fp32 (row stride ldc).
+// A (m, K), B (n, K) row-major 16-bit (bf16, or fp16 when fp16 != 0), C fp32 or (c_bf16 != 0) bf16, row stride ldc
+// elements.
 int tc_gemm_nt(const void* A, long long m, long long lda, const void* B, long long n, long long ldb, long long K,
-               int fp16, const float* row_add, const float* col_add, float* C, long long ldc, cudaStream_t st);
+               int fp16, const float* row_add, const float* col_add, void* C, long long ldc, int c_bf16,
+               cudaStream_t st);
 }  // namespace ktf

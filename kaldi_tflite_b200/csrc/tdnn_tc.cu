@@ -57,6 +57,8 @@ constexpr int kRowSeg = 64;                          // bytes of one output row 
 constexpr int kStgPitch = kRowSeg + 16;              // staged row pitch: payload + 16 B (bank spread)
 constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch;  // per-warp 32-row transpose buffers for coalesced stores
 constexpr int kSmemTc = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kVecBytes + kSegBytes + kStgBytes;
+static_assert((kStages * kStageBytes) % 512 == 0 && (32 * kStgPitch) % 512 == 0,
+              "staging buffers are TMA-store sources with the 64-byte swizzle: 512-byte aligned");
 
 enum { kModeBf16 = 0, kModeF32 = 1, kModeStats = 2 };
 
@@ -88,6 +90,7 @@ struct TcArgs {
   const long long* rows_dev;  // optional: the ACTUAL number of activation rows, read on the device (m_rows, or n_rows
                               // when shift_b); the host value is then only an upper bound (VAD-compacted batches: no
                               // host round trip for the kept-row count)
+  int tma_store;            // rows are written with TMA tensor stores (tmC is valid; see store_chunk)
   int reverse;              // walk the tiles from the last row block to the first (see launch_gemm)
   int debug;                // development knobs (KTF_TC_DEBUG): 1 = skip global stores, 2 = skip the epilogue math
 };
@@ -136,6 +139,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 // requested one whole tile ahead with a single bulk prefetch.
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// TMA tensor store of one staged box (smem -> global) as a bulk async-group; the staging buffer may be rewritten once
+// tma_store_wait_read() has returned (the group has finished READING shared memory).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
+               "cp.async.bulk.commit_group;\n" ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+// generic-proxy writes to shared memory (the staging STS) -> visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
 
 // K-major, 128B-swizzled operand tile: rows of 64 16-bit elements (128 B), 8-row groups 1024 B apart.
@@ -210,7 +228,8 @@ __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
 template <bool OUT_BF16, bool VEC>
 __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float* vb, float relu_lo, float radd,
                                             unsigned char* stg, int lane, int flags, bool plain, unsigned char* out0,
-                                            long long ld_bytes, int cols_left) {
+                                            long long ld_bytes, int cols_left, const CUtensorMap* tmC, int tma_col,
+                                            int tma_row, bool& tma_pending) {
   const float4* b4 = reinterpret_cast<const float4*>(vb);
   const float4* s4 = reinterpret_cast<const float4*>(vb + BN);
   const float4* o4 = reinterpret_cast<const float4*>(vb + 2 * BN);
@@ -218,14 +237,19 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
   constexpr int kCols = kRowSeg / (kPacked ? 2 : 4);   // columns per staged row segment
   constexpr int kPieces = kRowSeg / 16;            // 16-byte pieces per row segment
   constexpr int kEs = OUT_BF16 ? 2 : 4;
-#pragma unroll
   constexpr int kPitch = VEC ? kRowSeg : kStgPitch;
-  const int wsw = (lane >> 1) & 3;                 // swizzle of my own row (VEC)
+  constexpr int kGroups = kCols / 8;               // groups of 8 columns per pass
+  const int wsw = (lane >> 1) & 3;                 // swizzle of my own row (VEC): the 64-byte TMA swizzle pattern
+  // `plain` VEC blocks (all 32 rows stored, no halo replicas) leave through a TMA tensor store of the staged box:
+  // no read-back, no per-lane global stores.  tmC == nullptr: st.global path.
+  const bool tma = VEC && plain && tmC != nullptr;
+#pragma unroll
   for (int pass = 0; pass < 32 / kCols; ++pass) {
     uint4* mine = reinterpret_cast<uint4*>(stg + lane * kPitch);
+    uint4 val[kPacked ? kGroups : 2 * kGroups];    // the math first: it covers the wait for the previous box
 #pragma unroll
-    for (int g = 0; g < kCols / 8; ++g) {          // 8 columns per group
-      const int c8 = pass * (kCols / 8) + g;       // which group of 8 columns of the chunk
+    for (int g = 0; g < kGroups; ++g) {            // 8 columns per group
+      const int c8 = pass * kGroups + g;           // which group of 8 columns of the chunk
       float x[8];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -236,15 +260,36 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
         x[4 * h + 3] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo), ss.w, oo.w);
       }
       if (kPacked) {
-        mine[g ^ wsw] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                   pack_bf16x2(x[6], x[7]));
+        val[g] = make_uint4(pack_bf16x2(x[0] + radd, x[1] + radd), pack_bf16x2(x[2] + radd, x[3] + radd),
+                            pack_bf16x2(x[4] + radd, x[5] + radd), pack_bf16x2(x[6] + radd, x[7] + radd));
+      } else {
+        val[2 * g] = make_uint4(__float_as_uint(x[0] + radd), __float_as_uint(x[1] + radd),
+                                __float_as_uint(x[2] + radd), __float_as_uint(x[3] + radd));
+        val[2 * g + 1] = make_uint4(__float_as_uint(x[4] + radd), __float_as_uint(x[5] + radd),
+                                    __float_as_uint(x[6] + radd), __float_as_uint(x[7] + radd));
+      }
+    }
+    if (tma_pending) {                             // warp-uniform: the previous box still reads the staging buffer
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+      tma_pending = false;
+    }
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      if (kPacked) {
+        mine[g ^ wsw] = val[g];
       } else {
         const int sw = VEC ? wsw : 0;
-        mine[(2 * g) ^ sw] = make_uint4(__float_as_uint(x[0] + radd), __float_as_uint(x[1] + radd),
-                                        __float_as_uint(x[2] + radd), __float_as_uint(x[3] + radd));
-        mine[(2 * g + 1) ^ sw] = make_uint4(__float_as_uint(x[4] + radd), __float_as_uint(x[5] + radd),
-                                            __float_as_uint(x[6] + radd), __float_as_uint(x[7] + radd));
+        mine[(2 * g) ^ sw] = val[2 * g];
+        mine[(2 * g + 1) ^ sw] = val[2 * g + 1];
       }
+    }
+    if (tma) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(tmC, stg, tma_col + pass * kCols, tma_row);
+      tma_pending = true;
+      continue;
     }
     __syncwarp();
     if (VEC) {
@@ -307,22 +352,23 @@ __device__ __forceinline__ void tile_coords(long long tile, long long m_tiles, i
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreadsTc, 1)
-tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const TcArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // 1024-byte alignment for the 128B swizzle; offsetting the __shared__ array (instead of rounding a generic
   // pointer) keeps the address space visible to the compiler, so the epilogue reads are LDS, not generic LD.
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + kStages * kABytes;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + kStages * kStageBytes);
+  unsigned char* s_stg = smem + kStages * kStageBytes;   // [kEpiWarps][32][kStgPitch], 512-byte aligned (TMA store source)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + kStages * kStageBytes + kStgBytes);
   unsigned long long* full_bar = bars;                       // [kStages]
   unsigned long long* empty_bar = bars + kStages;            // [kStages]
   unsigned long long* tfull_bar = bars + 2 * kStages;        // [kAccStages]
   unsigned long long* tempty_bar = tfull_bar + kAccStages;   // [kAccStages]
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty_bar + kAccStages);
-  float* s_vec = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [kAccStages][3][BN]
-  int* s_seg = reinterpret_cast<int*>(smem + kStages * kStageBytes + 256 + kVecBytes);  // [kAccStages][BN]
-  unsigned char* s_stg = smem + kStages * kStageBytes + 256 + kVecBytes + kSegBytes;    // [kEpiWarps][32][kStgPitch]
+  float* s_vec = reinterpret_cast<float*>(smem + kStages * kStageBytes + kStgBytes + 256);  // [kAccStages][3][BN]
+  int* s_seg = reinterpret_cast<int*>(smem + kStages * kStageBytes + kStgBytes + 256 + kVecBytes);  // [kAccStages][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long m_rows = a.m_rows, n_rows = a.n_rows;
@@ -362,6 +408,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
+      if (a.tma_store) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmC) : "memory");
       int stage = 0;
       unsigned phase = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -442,6 +489,8 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int colq = (warp - 2) >> 2;         // which kEpiCols of the tile's 256 columns
     const int et = threadIdx.x - 64;          // 0..255
     int staged_nt0 = -1, staged_nt1 = -1;     // n-tile whose epilogue vectors sit in s_vec[0] / s_vec[1]
+    bool tma_pending = false;                 // a TMA store of this warp may still be reading its staging buffer
+    const CUtensorMap* tmc = a.tma_store ? &tmC : nullptr;
     float pre_b = 0.0f, pre_s = 1.0f, pre_o = 0.0f;   // column (nt * BN + et) of bias / scale / offset, prefetched
     int pre_nt = -1;
     auto prefetch_vec = [&](int nt_) {
@@ -552,7 +601,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (a.debug & 1) flags = 0;
         const bool plain = __all_sync(0xffffffffu, flags == kRowStore);
         float radd = 0.0f;
-        if (MODE == kModeF32 && a.row_add != nullptr && row < m_rows) radd = a.row_add[row];
+        if (a.row_add != nullptr && row < m_rows) radd = a.row_add[row];
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
 
@@ -574,17 +623,20 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int col0 = col_base + cc;
           if (col0 >= n_cols || (a.debug & 2)) continue;  // warp-uniform
           unsigned char* out0 = owarp + (long long)col0 * kEs;
+          const int trow = (int)(mt * BM) + quarter * 32;
           if (vec_ok && col0 + 32 <= n_cols)
-            store_chunk<kBf16, true>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, plain, out0, ld_bytes, 32);
+            store_chunk<kBf16, true>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, plain, out0, ld_bytes, 32, tmc,
+                                     col0, trow, tma_pending);
           else
             store_chunk<kBf16, false>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, false, out0, ld_bytes,
-                                      n_cols - col0);
+                                      n_cols - col0, nullptr, 0, 0, tma_pending);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (tma_pending && lane == 0) tma_store_wait_read();   // shared memory must outlive the last box
   }
 
   tc_fence_before();
@@ -872,6 +924,24 @@ int encode_map(CUtensorMap* map, const void* base, unsigned long long inner, uns
   return KTF_OK;
 }
 
+// Output map for the TMA-store epilogue: row-major (rows, cols) matrix of 2-byte (bf16) or 4-byte (fp32) elements, boxes
+// of 32 rows x 64 bytes with the 64-byte swizzle (the layout store_chunk stages).  Returns false when the matrix cannot
+// be described (unaligned base / pitch): the epilogue then keeps its st.global path.
+bool encode_map_out(CUtensorMap* map, const void* base, int elem_bytes, unsigned long long cols, unsigned long long rows,
+                    unsigned long long ld_elems) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr || base == nullptr || rows == 0 || cols == 0) return false;
+  if ((reinterpret_cast<unsigned long long>(base) & 15ull) != 0 || ((ld_elems * elem_bytes) & 15ull) != 0) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(kRowSeg / elem_bytes), 32};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 int check_arch() {
@@ -913,8 +983,26 @@ void release_layer(TcLayer* L) {
   L->ws.release();
 }
 
+int tma_store_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("KTF_TC_TMA_STORE");     // development knob: 0 = st.global epilogue
+    on = e ? atoi(e) : 1;
+  }
+  return on;
+}
+
 template <int MODE>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args_in, cudaStream_t st) {
+  TcArgs args = args_in;
+  CUtensorMap tmC = tmA;                                // placeholder when the epilogue does not use it
+  args.tma_store = 0;
+  if (MODE != kModeStats && tma_store_enabled() && args.out != nullptr) {
+    const int es = (MODE == kModeBf16) ? 2 : 4;
+    if (encode_map_out(&tmC, args.out, es, (unsigned long long)args.n_rows, (unsigned long long)args.m_rows,
+                       (unsigned long long)args.out_ld))
+      args.tma_store = 1;
+  }
   static unsigned long long attr_done = 0;              // per device (function attributes are per context)
   if (ktf::first_use_on_device(&attr_done))
     KTF_CUDA(cudaFuncSetAttribute(tdnn_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc));
@@ -925,9 +1013,9 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& ar
     const char* e = getenv("KTF_TC_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
-  const_cast<TcArgs&>(args).debug = dbg;
+  args.debug = dbg;
   const unsigned grid = (unsigned)std::min<long long>(tiles, ktf::num_sms());
-  tdnn_tc_kernel<MODE><<<grid, kThreadsTc, kSmemTc, st>>>(tmA, tmB, args);
+  tdnn_tc_kernel<MODE><<<grid, kThreadsTc, kSmemTc, st>>>(tmA, tmB, tmC, args);
   KTF_LAUNCH_OK();
   return KTF_OK;
 }
@@ -1117,7 +1205,8 @@ int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in
 // C[i, j] = sum_k A[i, k] * B[j, k] + row_add[i] + col_add[j], A (m, K) and B (n, K) row-major 16-bit
 // (bf16 or fp16), C fp32 with row stride ldc.  K and both leading dimensions must be multiples of 8.
 int tc_gemm_nt(const void* A, long long m, long long lda, const void* B, long long n, long long ldb, long long K,
-               int fp16, const float* row_add, const float* col_add, float* C, long long ldc, cudaStream_t st) {
+               int fp16, const float* row_add, const float* col_add, void* C, long long ldc, int c_bf16,
+               cudaStream_t st) {
   int rc = check_arch();
   if (rc != KTF_OK) return rc;
   CUtensorMap tmA, tmB;
@@ -1135,7 +1224,7 @@ int tc_gemm_nt(const void* A, long long m, long long lda, const void* B, long lo
   args.row_add = row_add;
   args.out = C;
   args.out_ld = ldc;
-  return launch_gemm<kModeF32>(tmA, tmB, args, st);
+  return c_bf16 ? launch_gemm<kModeBf16>(tmA, tmB, args, st) : launch_gemm<kModeF32>(tmA, tmB, args, st);
 }
 
 }  // namespace ktf

@@ -241,6 +241,7 @@ class _Frontend:
                                             ctypes.byref(self.handle)))
         self.out_dim = N.lib().ktf_frontend_out_dim(self.handle)
         self.want_energy = bool(cfg.output == N.KTF_OUT_WINDOWED and cfg.use_energy)
+        self.dither = float(cfg.dither)
 
     def __del__(self):
         try:
@@ -252,6 +253,12 @@ class _Frontend:
     def num_frames(self, n, snip_edges=True):
         return int(N.lib().ktf_frontend_num_frames_ex(self.handle, n, int(bool(snip_edges))))
 
+    def _ingest(self, wav):
+        # the dithering (generic) kernel takes float32 samples: raw PCM is widened first (dither != 0 only)
+        if self.dither != 0.0 and wav.dtype == torch.int16:
+            return wav.to(torch.float32)
+        return wav
+
     @staticmethod
     def _fmt(wav):
         if wav.dtype == torch.int16:
@@ -262,6 +269,7 @@ class _Frontend:
 
     def forward(self, wav, snip_edges=True):
         """wav CUDA float32 / int16 (B, n) -> (B, T, out_dim) [, (B, T, 1) energy]."""
+        wav = self._ingest(wav)
         B, n = wav.shape
         Tn = self.num_frames(n, snip_edges)
         out = torch.empty((B, Tn, self.out_dim), device=wav.device, dtype=torch.float32)
@@ -273,6 +281,7 @@ class _Frontend:
 
     def forward_ragged(self, wav_flat, sample_offsets, snip_edges=True):
         """wav_flat CUDA (total,), sample_offsets numpy int64 (B+1) -> (total_frames, out_dim), frame offsets."""
+        wav_flat = self._ingest(wav_flat)
         B = len(sample_offsets) - 1
         so = np.ascontiguousarray(sample_offsets, dtype=np.int64)
         fo = np.zeros(B + 1, dtype=np.int64)
@@ -334,27 +343,18 @@ class Windowing(Layer):
                                 raw_energy=int(self.rawEnergy), use_energy=int(self.returnEnergy),
                                 use_power=1, use_log_fbank=1, apply_lifter=0,
                                 preemphasis=float(self.preemphasisCoeff),
-                                energy_floor=float(self.energyFloor), epsilon=float(self.eps))
+                                energy_floor=float(self.energyFloor), epsilon=float(self.eps),
+                                dither=float(self.dither))
             self._fe[key] = _Frontend(cfg, window_function(self.windowType, width, self.blackmanCoeff))
         return self._fe[key]
 
     def call(self, inputs):
         fs, ref = _as_framed(inputs)
         self._maybe_build(fs.shape)
-        wav = _dithered(fs.wav, self.dither)
-        out, energy = self._frontend(fs.width, fs.shift).forward(wav, fs.snip_edges)
+        out, energy = self._frontend(fs.width, fs.shift).forward(fs.wav, fs.snip_edges)   # dither: inside the kernel
         if self.returnEnergy:
             return T.like_input(out, ref), T.like_input(energy, ref)
         return T.like_input(out, ref)
-
-
-def _dithered(wav, dither):
-    """windowing.py:182-183.  Dither is random by construction: statistically matched only
-    (torch Philox on the device), never bit-matched; parity runs use dither=0."""
-    if dither != 0.0:
-        wav = wav.to(torch.float32)
-        return wav + torch.randn_like(wav) * float(dither)
-    return wav
 
 
 # ------------------------------------------------------------------------------------------
@@ -421,7 +421,7 @@ class FilterBank(Layer):
                                 remove_dc_offset=0, raw_energy=1, use_energy=0,
                                 use_power=int(self.usePower), use_log_fbank=int(self.useLogFBank),
                                 apply_lifter=0, preemphasis=0.0, energy_floor=0.0,
-                                epsilon=float(self.eps))
+                                epsilon=float(self.eps), dither=0.0)
             self._fe[key] = _Frontend(cfg, np.ones(width, dtype=np.float32), bank)
         return self._fe[key]
 
@@ -539,7 +539,7 @@ class MFCC(Layer):
                                 use_energy=int(self.useEnergy), use_power=int(fb.usePower),
                                 use_log_fbank=int(fb.useLogFBank), apply_lifter=int(lifter_on),
                                 preemphasis=float(w.preemphasisCoeff), energy_floor=float(w.energyFloor),
-                                epsilon=float(self.eps))
+                                epsilon=float(self.eps), dither=float(w.dither))
             self._fe[key] = _Frontend(cfg, window_function(w.windowType, width, w.blackmanCoeff), bank,
                                       dct2_matrix(self.melBins, self.numMfccs),
                                       self.lifters if lifter_on else None)
@@ -548,8 +548,8 @@ class MFCC(Layer):
     def call(self, inputs):
         fs, ref = _as_framed(inputs)
         self._maybe_build(fs.shape)
-        wav = _dithered(fs.wav, self.windowing.dither)
-        out, _ = self.frontend(fs.width, fs.shift).forward(wav, fs.snip_edges)
+        # dither (windowing.py:182-183) is drawn per framed sample inside the kernel
+        out, _ = self.frontend(fs.width, fs.shift).forward(fs.wav, fs.snip_edges)
         return T.like_input(out, ref)
 
 

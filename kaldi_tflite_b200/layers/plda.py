@@ -109,15 +109,23 @@ class PLDA(Layer):
         N.check(N.lib().ktf_plda_transform(self.handle_for(num_examples), T.ptr(x2d), n, T.ptr(u), T.stream_ptr()))
         return u
 
-    def logLikelihoodRatio(self, u_test, u_enroll=None, out=None, num_examples=1.0):
+    def logLikelihoodRatio(self, u_test, u_enroll=None, out=None, num_examples=1.0, score_dtype=None):
         """scores[i, j] = LLR(test i | enrolled j): plda.py:215-245 (all-pairs); `num_examples` = utterances averaged
-        into each enrolled vector."""
+        into each enrolled vector.  `score_dtype=torch.bfloat16` (float32 layers only) writes the compact score matrix
+        of SURVEY 8f rank 3: the same fp32-equivalent value, rounded once to bfloat16 -- half the HBM write that bounds
+        all-vs-all scoring at dim 128."""
         u_enroll = u_test if u_enroll is None else u_enroll
         nt, ne = u_test.shape[0], u_enroll.shape[0]
+        compact = score_dtype is torch.bfloat16 or (out is not None and out.dtype is torch.bfloat16)
+        if score_dtype is not None and not compact and score_dtype != self.torchDtype:
+            raise ValueError(f"score_dtype must be {self.torchDtype} or torch.bfloat16")
+        if compact and self.paramDtype != np.float32:
+            raise ValueError("bfloat16 scores need a float32 PLDA layer")
         if out is None:
-            out = torch.empty((nt, ne), device=u_test.device, dtype=self.torchDtype)
-        N.check(N.lib().ktf_plda_score(self.handle_for(num_examples), T.ptr(u_test), nt, T.ptr(u_enroll), ne,
-                                       T.ptr(out), out.stride(0), T.stream_ptr()))
+            out = torch.empty((nt, ne), device=u_test.device, dtype=torch.bfloat16 if compact else self.torchDtype)
+        N.check(N.lib().ktf_plda_score_ex(self.handle_for(num_examples), T.ptr(u_test), nt, T.ptr(u_enroll), ne,
+                                          T.ptr(out), out.stride(0),
+                                          N.KTF_SCORES_BF16 if compact else N.KTF_SCORES_NATIVE, T.stream_ptr()))
         return out
 
     def call(self, inputs):

@@ -93,10 +93,7 @@ class XvectorExtractor:
     # ---- stages, all on ragged (rows, dim) layouts ------------------------------------
     def features(self, wav_flat, sample_offsets):
         """Fused framing + MFCC over a ragged batch -> (rows, num_mfccs), frame offsets (CUDA int64)."""
-        fe = self.mfcc.frontend(self.framing.frameWidth, self.framing.frameShift)
-        if self.mfcc.windowing.dither != 0.0:
-            wav_flat = wav_flat.to(torch.float32)
-            wav_flat = wav_flat + torch.randn_like(wav_flat) * float(self.mfcc.windowing.dither)
+        fe = self.mfcc.frontend(self.framing.frameWidth, self.framing.frameShift)   # dither: inside the kernel
         snip = self.framing.snipEdges
         lens = np.diff(sample_offsets)
         if len(lens) > 0 and bool(np.all(lens == lens[0])):

@@ -332,6 +332,49 @@ def test_set_weights_after_forward_is_applied(ktf):
 
 
 # ------------------------------------------------------------------------------------------------
+# dither drawn inside the kernel (windowing.py:182-183)
+# ------------------------------------------------------------------------------------------------
+
+def test_dither_in_kernel_is_per_framed_sample(ktf):
+    """The reference adds dither * N(0, 1) to the FRAMED tensor: overlapping frames do not share noise.  On silence,
+    with a rectangular window and no DC removal / pre-emphasis, the windowed frames ARE the noise."""
+    from kaldi_tflite_b200 import _native
+    x = np.zeros((4, 16000), np.float32)
+    fr = ktf.layers.Framing(dynamic_input_shape=True)
+    win = ktf.layers.Windowing(window_type="rectangular", dither=2.0, remove_dc_offset=False,
+                               preemphasis_coefficient=0.0, return_energy=False)
+    _native.lib().ktf_set_dither_seed(1234)
+    a = win(fr(x))
+    assert a.shape == (4, 98, 400)
+    z = a / 2.0
+    assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1.0) < 0.01
+    assert abs(float((z ** 3).mean())) < 0.03 and abs(float((z ** 4).mean()) - 3.0) < 0.1     # skewness, kurtosis
+    # frames t and t + 1 overlap in 240 samples: the shared samples must carry independent draws
+    shared_a, shared_b = z[:, :-1, 160:], z[:, 1:, :240]
+    corr = float(np.mean(shared_a * shared_b))
+    assert abs(corr) < 0.01, corr
+    # neighbouring samples / lanes are uncorrelated too
+    assert abs(float(np.mean(z[..., 1:] * z[..., :-1]))) < 0.01
+    # a new call draws new noise; the same seed reproduces the sequence of calls
+    b = win(fr(x))
+    assert abs(float(np.mean(a * b))) / 4.0 < 0.01
+    _native.lib().ktf_set_dither_seed(1234)
+    assert np.array_equal(win(fr(x)), a)
+    # pre-emphasis sees the DITHERED neighbour: y[i] = n[i] - 0.97 n[i-1] has variance (1 + 0.97^2) * dither^2
+    pre = ktf.layers.Windowing(window_type="rectangular", dither=1.0, remove_dc_offset=False,
+                               preemphasis_coefficient=0.97, return_energy=False)(fr(x))
+    assert abs(float(pre[..., 1:].var()) - (1.0 + 0.97 ** 2)) < 0.03
+    # MFCC of a loud signal barely moves with dither 1 (and the default YAML value runs end to end)
+    rng = np.random.default_rng(0)
+    loud = (rng.standard_normal((2, 16000)) * 3000).astype(np.float32)
+    m0 = ktf.layers.MFCC(num_mfccs=30, num_mels=30)(fr(loud))
+    m1 = ktf.layers.MFCC(num_mfccs=30, num_mels=30, dither=1.0)(fr(loud))
+    assert 0.0 < float(np.max(np.abs(m1 - m0))) < 0.05
+    m16 = ktf.layers.MFCC(num_mfccs=30, num_mels=30, dither=1.0)(fr(loud.astype(np.int16)))
+    assert float(np.max(np.abs(m16 - m0))) < 0.05
+
+
+# ------------------------------------------------------------------------------------------------
 # sharded PLDA, two ranks on one GPU
 # ------------------------------------------------------------------------------------------------
 
@@ -352,6 +395,58 @@ def test_plda_sharded_two_ranks_vs_oracle(tmp_path):
         assert r["ok"], r
         assert r["max_rel"] <= 1e-3, r
         assert r["launches"] > 0
+
+
+def _run_cabi_workers(tmp_path, nranks):
+    worker = os.path.join(ROOT, "tests", "cabi_plda_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(nranks), str(r), str(tmp_path)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(nranks)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o}"
+    res = []
+    for r in range(nranks):
+        with open(os.path.join(str(tmp_path), f"cabi_rank{r}.json")) as f:
+            res.append(json.load(f))
+    return res
+
+
+def test_cabi_context_and_collective_without_torch(tmp_path):
+    """ktf_ctx_* / ktf_nccl_allgather_xvec -- the sharded PLDA step driven by ctypes alone (no torch in the
+    worker process).  One rank always; two ranks over NCCL when the box has two GPUs."""
+    import torch
+    (r,) = _run_cabi_workers(tmp_path, 1)
+    assert r["max_rel"] <= 1e-3 and r["launches"] > 0 and not r["torch_loaded"], r
+    if torch.cuda.device_count() >= 2:
+        two = _run_cabi_workers(tmp_path, 2)
+        for r in two:
+            assert r["max_rel"] <= 1e-3 and r["nranks"] == 2 and not r["torch_loaded"], r
+
+
+def test_plda_compact_bf16_scores(ktf):
+    # SURVEY 8f rank 3: the score matrix as bfloat16 (half the HBM write): same fp32-equivalent value rounded once
+    import torch
+    dim, nt, ne = 128, 777, 1300
+    mean, Tm, psi = synthetic_plda(dim)
+    rng = np.random.default_rng(23)
+    x = rng.standard_normal((nt + ne, dim))
+    x = (x / np.linalg.norm(x, axis=1, keepdims=True) * np.sqrt(dim)).astype(np.float32)
+    layer = ktf.layers.PLDA(dim, mean, Tm, psi, dtype=np.float32, return_transformed=False)
+    u = layer.transformVector(torch.from_numpy(x).cuda())
+    full = layer.logLikelihoodRatio(u[:nt], u[nt:])
+    got = layer.logLikelihoodRatio(u[:nt], u[nt:], score_dtype=torch.bfloat16)
+    assert got.dtype is torch.bfloat16 and tuple(got.shape) == (nt, ne)
+    assert torch.equal(got, full.to(torch.bfloat16))            # exactly the fp32 score rounded to nearest-even
+    uo = O.plda_transform(x, mean, Tm, psi, dtype=np.float64)
+    want = O.plda_llr(uo, psi)[:nt, nt:]
+    err = np.abs(got.float().cpu().numpy() - want)
+    assert np.all(err <= 2.0 ** -8 * np.abs(want) + 1e-3)
+    # into a strided, preallocated block (the sharded path writes column blocks)
+    big = torch.zeros((nt, ne + 40), device="cuda", dtype=torch.bfloat16)
+    layer.logLikelihoodRatio(u[:nt], u[nt:], out=big[:, 8:8 + ne])
+    assert torch.equal(big[:, 8:8 + ne], got) and float(big[:, :8].abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        ktf.layers.PLDA(dim, mean, Tm, psi, dtype=np.float64).logLikelihoodRatio(u.double(), score_dtype=torch.bfloat16)
 
 
 # ------------------------------------------------------------------------------------------------

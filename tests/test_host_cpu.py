@@ -147,7 +147,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == set(_native.exported_symbols())
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.ktf_version() == 100
+    assert lib.ktf_version() == 101
 
 
 def test_product_never_imports_oracle():
