@@ -526,21 +526,33 @@ def stage_wav2xvec(h, steps, warmup, batch=BATCH):
     _, inter = ext(wav, return_intermediate=True)
     kept = int(inter["voiced_offsets"][-1].item())           # outside the timed region: for the FLOP count only
     assert ext.xvec._stack is not None, "the TDNN stack is not on the tcgen05 engine"
+    stack = ext.xvec.fused_vad_cmvn_stack(30)
+    assert stack is not None, "the fused VAD / CMVN / splice pre-pass does not apply"
+    fuse = os.environ.get("KTF_BENCH_FUSE", "1") != "0"
+    ext.fusePrepass = fuse
 
     def step(pairs):
         if pairs is None:
             ext(wav)
             return
-        # exactly ext(wav) (models/xvector_extractor.py), with an event pair around the TDNN stack; nothing in it
-        # synchronises with the host (the kept-row count after VAD stays on the device)
+        # exactly ext(wav) (models/xvector_extractor.py: features -> embed -> backend), with an event pair around the
+        # TDNN stack; nothing in it synchronises with the host (the kept-row count after VAD stays on the device)
         feats, offsets = ext.features(*ext._flatten(wav))
         mask = ext.vad.mask_ragged(feats, offsets)
-        voiced, voffs, _ = ext.vad.compact_ragged(feats, mask, offsets, gather=True)
-        normed, _ = ext.cmvn.forward_ragged(voiced, voffs, max_frames=FRAMES)
-        a, b = ev_pair(torch)
-        a.record()
-        emb, _ = ext.xvec.forward_ragged(normed, voffs)     # the TDNN stack: 7 tcgen05 GEMM launches
-        b.record()
+        if fuse:
+            _, voffs, index = ext.vad.compact_ragged(feats, mask, offsets, gather=False)
+            a, b = ev_pair(torch)
+            a.record()
+            # the tcgen05 stack: VAD gather + CMVN + splice pre-pass, 6 GEMM launches, statistics finalize
+            emb = stack.forward_vad(feats, index, voffs, FRAMES, ext.cmvn.N)
+            b.record()
+        else:                                                  # development A/B: separate gather / CMVN / splice kernels
+            voiced, voffs, _ = ext.vad.compact_ragged(feats, mask, offsets, gather=True)
+            normed, _ = ext.cmvn.forward_ragged(voiced, voffs, max_frames=FRAMES)
+            a, b = ev_pair(torch)
+            a.record()
+            emb, _ = ext.xvec.forward_ragged(normed, voffs)
+            b.record()
         pairs.append((a, b))
         ext.backend(emb)
     ms, launches, clocks, tdnn_ms = h.timed(step, steps, warmup)

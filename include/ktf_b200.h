@@ -292,6 +292,20 @@ int32_t ktf_tdnn_stack_out_dim(const ktf_tdnn_stack* s);
 int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int64_t* offsets_dev,
                            int64_t batch, int64_t total_rows, float* out_dev, void* stream);
 
+/* wav -> x-vector form of the stack (models/kaldi/xvector_extractor.py:162-171): the VAD compaction (tf.gather_nd, :163-165),
+ * the sliding CMVN (layers/normalization/cmvn.py:186-250 with center=True, norm_vars=False, padding SAME) and the splice
+ * of the first layer are ONE pre-pass kernel in front of the GEMMs -- the kept rows are gathered into shared memory
+ * through the VAD index list, normalised there and leave as the bf16 operand of the first layer.
+ *   feats_dev   (all_rows, D0) un-normalised features (MFCCs before VAD)
+ *   index_dev   row index (into feats_dev) of every kept frame, in compacted order (ktf_vad_compact), or NULL when
+ *               feats_dev already holds the compacted rows
+ *   offsets_dev compacted frame offsets (batch + 1, device); total_rows >= offsets_dev[batch] (upper bound)
+ *   max_frames  any upper bound on the longest compacted utterance (sizes the grid)
+ * Requires a first layer with consecutive contexts; other CMVN modes: ktf_cmvn_forward + ktf_tdnn_stack_forward. */
+int ktf_tdnn_stack_forward_vad(ktf_tdnn_stack* s, const float* feats_dev, const int64_t* index_dev,
+                               const int64_t* offsets_dev, int64_t batch, int64_t total_rows, int64_t max_frames,
+                               int32_t cmvn_window, float* out_dev, void* stream);
+
 /* Element-wise helpers for callers that use ReLU / BatchNorm as stand-alone layers. */
 int ktf_relu_forward(const float* x_dev, int64_t n, float* y_dev, void* stream);
 int ktf_scale_offset_forward(const float* x_dev, int64_t rows, int32_t dim,

@@ -826,6 +826,209 @@ splice_eval_kernel(const float* __restrict__ x, int D, const long long* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fused pre-pass of the wav -> x-vector path: VAD gather -> sliding CMVN -> bf16 splice of the first layer.
+// Replaces three passes over the same rows -- the tf.gather_nd compaction of models/kaldi/xvector_extractor.py:163-165,
+// layers/normalization/cmvn.py:186-250 (center=True, norm_vars=False, padding SAME) and the materialised splice of
+// layers/tdnn/tdnn.py:251-258 for a first layer with consecutive contexts -- with one kernel: the kept MFCC rows are
+// gathered straight into shared memory through the VAD index list, normalised there, and leave as the spliced bf16
+// operand of tdnn1 in the padded-row layout.
+//
+// grid (batch, ceil(max_frames / tc)), 256 threads.  A CTA owns frames [c0, c1) of the COMPACTED utterance b:
+//   1. stage rows [lo, hi) -- every row a window of its frames (and of the +-halo frames its splice taps reach) needs --
+//      with 8-byte cp.async through index[] (or contiguously when index == nullptr);
+//   2. copy the rows of frames [e0, e1) aside (y), then turn the staged rows into inclusive prefix sums per column:
+//      32-row local prefixes, one scan over the block totals, offsets folded in;
+//   3. y[t] -= (P[ws + N - 1] - P[ws - 1]) / N with ws = clamp(t - N/2, 0, T - N)   (cmvn.py:172-204; T <= N: the
+//      global mean, :214-222);
+//   4. emit out[p, k * D + d] = y[clamp(t + ctx0 + k)][d] as bf16, 16 bytes per thread and step.
+// The prefix sums are differences of fp32 numbers up to ~N * |x|: their rounding (<= 2^-10 at 10^4) is divided by N again
+// in the mean, i.e. ~3e-6 on features of magnitude 20 -- the reference's own fp32 cumsum over the whole utterance
+// (cmvn.py:172) is coarser.
+constexpr int kPreThreads = 256;
+constexpr int kPreWarps = kPreThreads / 32;
+constexpr int kPreBlk = 32;
+
+// i / d for 0 <= i < 2^20 and 1 <= d <= 2^10 with one multiply: m = floor(2^32 / d) + 1 (host), exact in that range.
+__device__ __forceinline__ unsigned fast_div(unsigned i, unsigned m) { return __umulhi(i, m); }
+
+__global__ void __launch_bounds__(kPreThreads)
+gather_cmvn_splice_kernel(const float* __restrict__ feats, int dim, const long long* __restrict__ index,
+                          const long long* __restrict__ voffs, int window, int tc, int K, int ctx0,
+                          __nv_bfloat16* __restrict__ out, long long ld, unsigned magic_half, unsigned magic_chunks) {
+  extern __shared__ __align__(16) float spre[];
+  const long long b = blockIdx.x;
+  const long long r0 = voffs[b];
+  const int T = (int)(voffs[b + 1] - r0);
+  const int c0 = blockIdx.y * tc;
+  if (T <= 0 || c0 >= T) return;
+  const int c1 = min(c0 + tc, T);
+  const int halo_l = ctx0 < 0 ? -ctx0 : 0, halo_r = (ctx0 + K - 1) > 0 ? (ctx0 + K - 1) : 0;
+  const int e0 = max(c0 - halo_l, 0), e1 = min(c1 + halo_r, T);   // frames whose normalised rows the splice reads
+  const int N = window;
+  const bool global_stats = T <= N;
+  const int lo = global_stats ? 0 : min(max(e0 - N / 2, 0), T - N);
+  const int hi = global_stats ? T : min(max(e1 - 1 - N / 2, 0), T - N) + N;
+  const int R = hi - lo;
+  const int max_rows = tc + 2 * kHalo + N;
+  float* sx = spre;                                                             // [R][dim] staged rows
+  float* sy = spre + (((size_t)max_rows * dim + 3) & ~(size_t)3);               // [e1 - e0][dim] normalised rows (+ 8 pad)
+  float* bsum = sy + (((size_t)(tc + 2 * kHalo) * dim + 8 + 3) & ~(size_t)3);   // [nblk][dim] sums of 32-row blocks
+  long long* srow = reinterpret_cast<long long*>(bsum + (size_t)(max_rows / kPreBlk + 2) * dim + (dim & 1));   // [R]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- 1. stage (gather): source rows first (independent loads, one latency), then the copies ----------------
+  for (int r = tid; r < R; r += kPreThreads) srow[r] = index ? index[r0 + lo + r] : (r0 + lo + r);
+  __syncthreads();
+  if ((dim & 1) == 0) {
+    const unsigned half = (unsigned)dim >> 1;                  // 8-byte pieces: rows start 8-byte aligned
+    const unsigned sbase = smem_u32(sx);
+    const unsigned total = (unsigned)R * half;
+    for (unsigned i = tid; i < total; i += kPreThreads) {
+      const unsigned r = fast_div(i, magic_half), h = i - r * half;
+      const float* src = feats + srow[r] * dim + 2 * h;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sbase + 8u * i), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+  } else {
+    for (int r = warp; r < R; r += kPreWarps) {
+      const float* src = feats + srow[r] * dim;
+      for (int d = lane; d < dim; d += 32) sx[r * dim + d] = src[d];
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. column sums of 32-row blocks: a warp's first window is then a handful of block sums plus the rows that
+  //         stick out on both sides (the arithmetic of cmvn_staged_kernel, vad_cmvn.cu) ----------------------------
+  const float* xs = sx - (long long)lo * dim;                  // xs[t * dim + d] = row t of the compacted utterance
+  const int nblk = R / kPreBlk;
+  for (int k = warp; k < nblk; k += kPreWarps) {
+    for (int d = lane; d < dim; d += 32) {
+      const float* col = sx + (k * kPreBlk) * dim + d;
+      float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+#pragma unroll
+      for (int r = 0; r < kPreBlk; r += 4) {
+        p0 += col[r * dim]; p1 += col[(r + 1) * dim]; p2 += col[(r + 2) * dim]; p3 += col[(r + 3) * dim];
+      }
+      bsum[k * dim + d] = (p0 + p1) + (p2 + p3);
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. y[t] = x[t] - mean over the window of t (cmvn.py:172-204; T <= N: the global mean, :214-222) ---------
+  {
+    const int per = (e1 - e0 + kPreWarps - 1) / kPreWarps;
+    const int t0 = e0 + warp * per, t1 = min(t0 + per, e1);
+    const int W = global_stats ? T : N, H = N / 2;
+    const float inv_n = 1.0f / (float)W;
+    for (int d = lane; d < dim && t0 < t1; d += 32) {
+      int ws = global_stats ? 0 : min(max(t0 - H, 0), T - N);
+      float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+      {
+        // rows [ws, ws + W) = leading rows up to the next block boundary, whole blocks, trailing rows
+        const int a0 = ws - lo;
+        const int kb = (a0 + kPreBlk - 1) / kPreBlk;
+        const int ke = min((a0 + W) / kPreBlk, nblk);
+        int r_lead_end = ws + W, r_trail = ws + W;               // no whole block inside: everything is "leading"
+        if (ke > kb) {
+          r_lead_end = lo + kb * kPreBlk;
+          r_trail = lo + ke * kPreBlk;
+          int k = kb;
+          for (; k + 2 <= ke; k += 2) { p0 += bsum[k * dim + d]; p1 += bsum[(k + 1) * dim + d]; }
+          if (k < ke) p0 += bsum[k * dim + d];
+        }
+        for (int r = ws; r < r_lead_end; ++r) p2 += xs[(long long)r * dim + d];
+        for (int r = r_trail; r < ws + W; ++r) p3 += xs[(long long)r * dim + d];
+      }
+      float sacc = (p0 + p1) + (p2 + p3);
+      float* yrow = sy + (t0 - e0) * dim + d;
+      int tt = t0;
+      if (global_stats) {
+        for (; tt < t1; ++tt, yrow += dim) *yrow = xs[tt * dim + d] - sacc * inv_n;
+      } else {
+        // head: frames whose window is still clamped at the start of the utterance
+        for (; tt < t1 && tt - H <= ws; ++tt, yrow += dim) *yrow = xs[tt * dim + d] - sacc * inv_n;
+        // interior: the window advances by exactly one row per frame
+        const int t_mid = min(t1, T - N + H + 1);
+        const float* po = xs + ws * dim + d;                     // row leaving the window
+        const float* pn = po + N * dim;                          // row entering it
+        const float* px = xs + tt * dim + d;
+#pragma unroll 4
+        for (; tt < t_mid; ++tt) {
+          sacc += *pn - *po;
+          po += dim; pn += dim;
+          *yrow = *px - sacc * inv_n;
+          px += dim; yrow += dim;
+        }
+        // tail: window clamped at the end of the utterance
+        for (; tt < t1; ++tt, yrow += dim) *yrow = xs[tt * dim + d] - sacc * inv_n;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 4. spliced bf16 rows of frames [c0, c1): the K taps of an interior frame are K * dim CONSECUTIVE floats of y
+  const unsigned chunks = (unsigned)(ld >> 3);
+  const int cols = K * dim;
+  const long long p_first = r0 + 2LL * kHalo * b + kHalo;     // padded row of frame 0
+  const unsigned total_chunks = (unsigned)(c1 - c0) * chunks;
+  for (unsigned i = tid; i < total_chunks; i += kPreThreads) {
+    const unsigned tt = fast_div(i, magic_chunks), q = i - tt * chunks;
+    const int t = c0 + (int)tt, col0 = (int)(q << 3);
+    const int ta = t + ctx0;
+    float f[8];
+    if (ta >= 0 && ta + K - 1 <= T - 1) {
+      const float* row = sy + (ta - e0) * dim + col0;           // may run up to 7 floats past the taps: masked below
+      if ((dim & 1) == 0) {
+        const float2* src = reinterpret_cast<const float2*>(row);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 v = src[u];
+          f[2 * u] = v.x;
+          f[2 * u + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] = row[u];
+      }
+      if (col0 + 8 > cols) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] = (col0 + u < cols) ? f[u] : 0.0f;
+      }
+    } else {                                                    // the first / last frames of the utterance
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = col0 + u;
+        f[u] = 0.0f;
+        if (c < cols) {
+          const int k = c / dim, d = c - k * dim;
+          const int src_t = min(max(ta + k, 0), T - 1);         // edge replication (tdnn.py:244-247)
+          f[u] = sy[(src_t - e0) * dim + d];
+        }
+      }
+    }
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __float2bfloat16_rn(f[u]);
+    *reinterpret_cast<uint4*>(out + (p_first + t) * ld + col0) = *reinterpret_cast<const uint4*>(v);
+  }
+  // halo rows of the operand only feed accumulator rows the GEMM epilogue never stores; keep them finite
+  if (c0 == 0 && warp < kHalo)
+    for (unsigned q = lane; q < chunks; q += 32)
+      *reinterpret_cast<uint4*>(out + (p_first - kHalo + warp) * ld + (q << 3)) = make_uint4(0, 0, 0, 0);
+  if (c1 == T && warp >= kPreWarps - kHalo)
+    for (unsigned q = lane; q < chunks; q += 32)
+      *reinterpret_cast<uint4*>(out + (p_first + T + (warp - (kPreWarps - kHalo))) * ld + (q << 3)) = make_uint4(0, 0, 0, 0);
+}
+
+size_t prepass_smem_bytes(int tc, int window, int dim) {
+  const size_t a = (((size_t)(tc + 2 * kHalo + window) * dim + 3) & ~(size_t)3);
+  const size_t y = (((size_t)(tc + 2 * kHalo) * dim + 8 + 3) & ~(size_t)3);
+  const size_t blk = (size_t)((tc + 2 * kHalo + window) / kPreBlk + 2) * dim + (dim & 1);
+  return (a + y + blk) * sizeof(float) + (size_t)(tc + 2 * kHalo + window) * sizeof(long long);
+}
+
 // (batch, 2, U) raw sums of r = relu(acc + bias) over the frames of each utterance -> mean || std of
 // y = scale * r + offset (batchnorm.py:81-88 folded in algebraically; stats_pooling.py:228-240):
 //   mean_y = scale * mean_r + offset,  var_y = scale^2 * (E[r^2] - mean_r^2),  std = sqrt(relu(var_y) + eps)
@@ -1285,11 +1488,18 @@ int32_t ktf_tdnn_stack_out_dim(const ktf_tdnn_stack* s) {
   return dim;
 }
 
-int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int64_t* offsets_dev,
-                           int64_t batch, int64_t total_rows, float* out_dev, void* stream) {
-  KTF_CHECK_ARG(s && feats_dev && offsets_dev && out_dev, "ktf_tdnn_stack_forward: null argument");
+}  // extern "C"
+
+// Shared body of ktf_tdnn_stack_forward (pre = nullptr) and ktf_tdnn_stack_forward_vad (fused pre-pass).
+struct StackPre {
+  const long long* index;   // kept-row indices into feats (or nullptr = rows are already compacted)
+  long long max_frames;     // upper bound on the longest compacted utterance
+  int cmvn_window;
+};
+
+static int stack_forward_impl(ktf_tdnn_stack* s, const float* feats_dev, const int64_t* offsets_dev, int64_t batch,
+                              int64_t total_rows, float* out_dev, const StackPre* pre, cudaStream_t st) {
   if (batch <= 0 || total_rows <= 0) return KTF_OK;
-  cudaStream_t st = (cudaStream_t)stream;
   const long long prow = total_rows + 2LL * kHalo * batch;
   const int nl = (int)s->layers.size();
   const long long* offs = (const long long*)offsets_dev;
@@ -1375,7 +1585,22 @@ int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int6
       __nv_bfloat16* sp = buf[which];
       const long long ld = round_up(cols, 8);
       const unsigned grid = blocks_for(prow * (ld >> 3), 256);
-      if (i == 0) {
+      if (i == 0 && pre != nullptr) {
+        // VAD gather + sliding CMVN + splice in one pass (the rows never exist as a gathered / normalised fp32 matrix)
+        const long long gys = (pre->max_frames + 255) / 256;
+        const int tc = (int)((((pre->max_frames + gys - 1) / gys) + 1) & ~1LL);
+        const size_t smem = prepass_smem_bytes(tc, pre->cmvn_window, L.D);
+        KTF_CHECK_ARG(smem <= 113 * 1024 && gys <= 65535, "CMVN window %d x dim %d does not fit the fused pre-pass",
+                      pre->cmvn_window, L.D);
+        static unsigned long long attr_set = 0;
+        if (ktf::first_use_on_device(&attr_set))
+          KTF_CUDA(cudaFuncSetAttribute(gather_cmvn_splice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        const unsigned half = (unsigned)std::max(L.D / 2, 1), chunks = (unsigned)(ld >> 3);
+        gather_cmvn_splice_kernel<<<dim3((unsigned)batch, (unsigned)gys), kPreThreads, smem, st>>>(
+            feats_dev, L.D, pre->index, offs, pre->cmvn_window, tc, L.K, L.ctx[0], sp, ld,
+            (unsigned)(0x100000000ull / half) + 1u, (unsigned)(0x100000000ull / chunks) + 1u);
+        KTF_LAUNCH_OK();
+      } else if (i == 0) {
         if ((rc = ktf::launch_splice_f32(L, feats_dev, offs, poffs, rowmap, rowseg, prow, prow_dev, sp, ld, st)) != KTF_OK)
           return rc;
       } else {
@@ -1424,6 +1649,28 @@ int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int6
     which ^= 1;
   }
   return KTF_OK;
+}
+
+extern "C" {
+
+int ktf_tdnn_stack_forward(ktf_tdnn_stack* s, const float* feats_dev, const int64_t* offsets_dev,
+                           int64_t batch, int64_t total_rows, float* out_dev, void* stream) {
+  KTF_CHECK_ARG(s && feats_dev && offsets_dev && out_dev, "ktf_tdnn_stack_forward: null argument");
+  return stack_forward_impl(s, feats_dev, offsets_dev, batch, total_rows, out_dev, nullptr, (cudaStream_t)stream);
+}
+
+int ktf_tdnn_stack_forward_vad(ktf_tdnn_stack* s, const float* feats_dev, const int64_t* index_dev,
+                               const int64_t* offsets_dev, int64_t batch, int64_t total_rows, int64_t max_frames,
+                               int32_t cmvn_window, float* out_dev, void* stream) {
+  KTF_CHECK_ARG(s && feats_dev && offsets_dev && out_dev, "ktf_tdnn_stack_forward_vad: null argument");
+  KTF_CHECK_ARG(cmvn_window > 0 && max_frames > 0, "`window` and `min_window` must be > 0");
+  const TcLayer& L0 = *static_cast<const TcLayer*>(s->layers[0]->tc);
+  bool ok = true;
+  for (int k = 1; k < L0.K; ++k) ok = ok && (L0.ctx[k] == L0.ctx[0] + k);
+  for (int k = 0; k < L0.K; ++k) ok = ok && L0.ctx[k] >= -kHalo && L0.ctx[k] <= kHalo;
+  KTF_CHECK_ARG(ok, "the fused VAD / CMVN pre-pass needs a first layer with consecutive contexts within +-%d", kHalo);
+  StackPre pre{(const long long*)index_dev, (long long)max_frames, cmvn_window};
+  return stack_forward_impl(s, feats_dev, offsets_dev, batch, total_rows, out_dev, &pre, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -132,6 +132,20 @@ class _Stack:
                                                T.stream_ptr()))
         return out
 
+    def can_fuse_vad_cmvn(self):
+        """First layer with consecutive contexts: the VAD gather + CMVN + splice pre-pass applies."""
+        ctx = self.affines[0].context
+        return all(c == ctx[0] + k for k, c in enumerate(ctx)) and max(abs(c) for c in ctx) <= 4
+
+    def forward_vad(self, feats2d, index, offsets, max_frames, cmvn_window):
+        """Un-normalised features + VAD index list + compacted offsets -> stack output (ktf_tdnn_stack_forward_vad)."""
+        rows, _ = feats2d.shape
+        B = offsets.numel() - 1
+        out = torch.empty((B if self.pools else rows, self.out_dim), device=feats2d.device, dtype=torch.float32)
+        N.check(N.lib().ktf_tdnn_stack_forward_vad(self.handle, T.ptr(feats2d), T.ptr(index), T.ptr(offsets), B, rows,
+                                                   int(max_frames), int(cmvn_window), T.ptr(out), T.stream_ptr()))
+        return out
+
 
 def glorot_uniform(shape, rng):
     """keras GlorotUniform: U(-l, l), l = sqrt(6 / (fan_in + fan_out)) (tdnn.py:50-51)."""

@@ -136,14 +136,21 @@ class Sequential:
                 i += 1
         return plan
 
-    def forward_ragged(self, x2d, offsets):
-        """x2d CUDA (rows, D); utterance b = rows offsets[b]..offsets[b+1].  Returns (y2d, offsets)."""
+    def _ensure_plan(self, feat_dim):
         if self._plan is None or self._plan_version != self._weights_version():
-            self._build_layers(x2d.shape[-1])
+            self._build_layers(feat_dim)
             self._plan = self._make_plan()
             self._plan_version = self._weights_version()
-            self._stack = None
             self._stack = self._try_stack(self._plan)       # None unless every layer runs on the tcgen05 engine
+
+    def fused_vad_cmvn_stack(self, feat_dim):
+        """The tcgen05 stack if it can take un-normalised features + a VAD index list directly (fused pre-pass)."""
+        self._ensure_plan(feat_dim)
+        return self._stack if (self._stack is not None and self._stack.can_fuse_vad_cmvn()) else None
+
+    def forward_ragged(self, x2d, offsets):
+        """x2d CUDA (rows, D); utterance b = rows offsets[b]..offsets[b+1].  Returns (y2d, offsets)."""
+        self._ensure_plan(x2d.shape[-1])
         B = offsets.numel() - 1
         if self._stack is not None:
             y = self._stack.forward_ragged(x2d, offsets)

@@ -57,6 +57,7 @@ class XvectorExtractor:
         weights (x-vectors are then meaningless: benchmarks / architecture tests only)."""
         self.name = name
         self.chunkSize = chunk_size
+        self.fusePrepass = True      # VAD gather + CMVN + splice as one kernel when the TDNN runs on the tcgen05 stack
         fr = dict(cfg["framing"])
         mf = dict(cfg["mfcc"])
         if dither is not None:
@@ -106,6 +107,17 @@ class XvectorExtractor:
 
     def embed(self, feats, offsets, max_frames=None):
         mask = self.vad.mask_ragged(feats, offsets)
+        stack = None
+        if self.fusePrepass and self.cmvn.padding == "SAME" and not self.cmvn.normVar:
+            stack = self.xvec.fused_vad_cmvn_stack(feats.shape[-1])
+        if stack is not None and stack.pools:
+            # tcgen05 stack: gather -> CMVN -> splice is ONE pre-pass kernel in front of the GEMMs; the kept rows are
+            # never written as a gathered / normalised fp32 matrix
+            _, voffs, index = self.vad.compact_ragged(feats, mask, offsets, gather=False)
+            self._no_voiced = (voffs[1:] == voffs[:-1]).any()
+            mf = feats.shape[0] if max_frames is None else max_frames
+            emb = stack.forward_vad(feats, index, voffs, mf, self.cmvn.N)
+            return emb, mask, voffs
         # `voiced` keeps the upper-bound row count; the kept-row count stays on the device (voffs[-1])
         voiced, voffs, _ = self.vad.compact_ragged(feats, mask, offsets, gather=True)
         # An utterance without voiced frames has no statistics to pool (the reference's gather_nd / reduce_mean

@@ -311,6 +311,36 @@ def test_wav2xvec_step_is_cuda_graph_capturable(ktf):
     assert float((out - eager).abs().max()) > 20 * float((out - want2).abs().max())   # it really is the new audio
 
 
+def test_fused_vad_cmvn_splice_prepass_equals_separate_kernels(ktf):
+    """ktf_tdnn_stack_forward_vad (one gather + CMVN + splice kernel in front of the GEMMs) against the separate
+    vad_gather / cmvn / splice kernels, on uniform and ragged batches, and against the oracle."""
+    cfg = extractor_cfg()
+    ext = ktf.models.XvectorExtractor(cfg, seed=0, allow_random_init=True)
+    wav = read_wav_int16(golden_path("librispeech_2.wav"))
+    noise = _gated_noise(6, seed=11)
+    batches = [noise, [wav[:80000], wav[80000:200000], noise[0][:40000], wav[150000:], wav[:8000], noise[1]]]
+    layers = sitw_layers_for_oracle(ext.xvec)
+    for x in batches:
+        ext.fusePrepass = True
+        n0 = ktf.launch_count()
+        fused = ext(x)
+        n_fused = ktf.launch_count() - n0
+        ext.fusePrepass = False
+        n0 = ktf.launch_count()
+        separate = ext(x)
+        n_sep = ktf.launch_count() - n0
+        assert n_fused == n_sep - 2                    # gather, CMVN and splice became one launch
+        for b in range(len(x)):
+            assert cosine(fused[b], separate[b]) > 0.999995, b
+            want = O.xvector_extractor(x[b], cfg, layers, ext.xvecGlobalMean, ext.ldaTransform)
+            assert cosine(fused[b], want) >= 0.9999, b
+    ext.fusePrepass = True
+    # an utterance shorter than the CMVN window (global mean branch, cmvn.py:214-222) and a batch of one
+    short = ext(wav[:30000])
+    want = O.xvector_extractor(wav[:30000], cfg, layers, ext.xvecGlobalMean, ext.ldaTransform)
+    assert cosine(short, want) >= 0.9999
+
+
 def test_set_weights_after_forward_is_applied(ktf):
     import yaml
     with open(os.path.join(ROOT, "data", "kaldi_models", "configs", "0008_sitw_v2_1a.yml")) as f:
