@@ -820,7 +820,7 @@ def stage_summary(name, st, pk):
         out.update({"n": st["n"], "allgather_ms": st["allgather_ms"], "allgather_bytes": st["allgather_bytes"],
                     "score_ms": st["score_ms"], "parity_max_rel": st["parity_max_rel"],
                     "bf16_scores": {"score_ms": st["score16_ms"],
-                                    "scores_per_sec": st["score_bytes"] / 4 * 1e3 / st["score16_ms"] * 1.0,
+                                    "scores_per_sec": float(st["n"]) * st["n"] / (st["score16_ms"] * 1e-3),
                                     "hbm_write_gbs": st["score_bytes"] / 2 / (st["score16_ms"] * 1e-3) / 1e9,
                                     "note": "compact output (2 bytes per trial), reported separately from the "
                                             "API-compatible float32 figure"},

@@ -99,6 +99,33 @@ struct Item {
   int nvalid;
 };
 
+// ---- TMA (bulk asynchronous copy) staging of a span: one elected lane issues a single cp.async.bulk of the whole span
+// (global -> shared, completion counted in bytes on the warp's mbarrier); no per-lane address arithmetic, no LSU
+// wavefronts for the fill.  Requires a 16-byte aligned source and a byte count that is a multiple of 16.
+__device__ __forceinline__ void span_mbar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void span_bulk_load(void* smem_dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                   "r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(src), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void span_mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(b), "r"(parity)
+        : "memory");
+  }
+}
+
 __device__ __forceinline__ Item decode_item(const FrontendArgs& a, long long item) {
   Item it;
   long long q, utt_frames;

@@ -252,12 +252,35 @@ __global__ void __launch_bounds__(kR16Threads, KTF_R16_MINB) frontend_r16_kernel
   const int LMS = DCT_REG ? 36 : ((M + 3) & ~3) + 4;   // log-mel row stride (one spare slot for padding units)
   const int out_row = (OUTPUT == KTF_OUT_MFCC) ? a.Kc : M;
   const int out_sz = (4 * out_row + 3) & ~3;
-  const int warp_floats = (span_p + 4 * kTile + 4 * LMS + out_sz + 31) & ~31;   // 128-byte aligned per-warp regions
+  const int warp_floats = (span_p + 4 * kTile + 4 * LMS + out_sz + 2 + 31) & ~31;   // 128-byte aligned per-warp regions
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s_span = s_warp0 + warp * warp_floats;
   float* s_T = s_span + span_p;
   float* s_LM = s_T + 4 * kTile;             // mel sums, then log-mel [f][LMS]
   float* s_out = s_LM + 4 * LMS;
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_out + ((out_sz + 1) & ~1));   // span mbarrier
+  unsigned bar_parity = 0;                   // phase of the NEXT TMA completion to wait for
+  bool cur_tma = false;                      // the span of `cur` was requested with a bulk copy (else cp.async)
+  if (lane == 0) span_mbar_init(s_bar);
+  __syncwarp();
+  // Stages the span of `it`: ONE bulk asynchronous copy (TMA) when it lies inside the utterance and is 16-byte aligned --
+  // every interior item of the 16 kHz geometry -- else the per-lane cp.async / mirrored path.
+  auto stage = [&](const Item& it) {
+    const long long s0 = it.frame0 * a.shift - a.edge_off;
+    const unsigned bytes = (unsigned)a.span * (PCM16 ? 2u : 4u);
+    const char* src = PCM16 ? reinterpret_cast<const char*>(a.wav16 + it.utt_base + s0)
+                            : reinterpret_cast<const char*>(a.wav + it.utt_base + s0);
+    const bool bulk = s0 >= 0 && it.utt_len - s0 >= a.span && (bytes & 15u) == 0 &&
+                      (reinterpret_cast<unsigned long long>(src) & 15ull) == 0;
+    if (bulk) {
+      if (lane == 0) span_bulk_load(s_span, src, bytes, s_bar);
+    } else if (PCM16) {
+      stage_span16(a, it, reinterpret_cast<short*>(s_span), lane);
+    } else {
+      stage_span(a, it, s_span, lane);
+    }
+    return bulk;
+  };
 
   const long long warp_global = (long long)blockIdx.x * kR16Warps + warp;
   const long long warp_stride = (long long)gridDim.x * kR16Warps;
@@ -266,7 +289,7 @@ __global__ void __launch_bounds__(kR16Threads, KTF_R16_MINB) frontend_r16_kernel
   long long item = warp_global;
   if (item < a.total_groups) {
     cur = decode_item(a, item);
-    if (PCM16) stage_span16(a, cur, reinterpret_cast<short*>(s_span), lane); else stage_span(a, cur, s_span, lane);
+    cur_tma = stage(cur);
   }
   for (int i = threadIdx.x; i < a.r16_blob_floats; i += kR16Threads) smem[i] = a.r16_blob[i];
   for (int i = lane; i < 4 * LMS; i += 32) s_LM[i] = 0.0f;   // slots >= M stay finite
@@ -322,8 +345,13 @@ __global__ void __launch_bounds__(kR16Threads, KTF_R16_MINB) frontend_r16_kernel
   }
 
   for (; item < a.total_groups; item += warp_stride) {
-    cp_async_wait_all();
-    __syncwarp();
+    if (cur_tma) {
+      span_mbar_wait(s_bar, bar_parity);
+      bar_parity ^= 1u;
+    } else {
+      cp_async_wait_all();
+      __syncwarp();
+    }
 
     // ---- windowing (windowing.py:180-209): rows of 32 samples, lane j owns samples 4j .. 4j+3 of a row
     float2 ze[16], zo[16];
@@ -388,7 +416,7 @@ __global__ void __launch_bounds__(kR16Threads, KTF_R16_MINB) frontend_r16_kernel
       const long long nxt = item + warp_stride;
       if (nxt < a.total_groups) {
         cur = decode_item(a, nxt);
-        if (PCM16) stage_span16(a, cur, reinterpret_cast<short*>(s_span), lane); else stage_span(a, cur, s_span, lane);
+        cur_tma = stage(cur);
       }
     }
 
@@ -672,7 +700,7 @@ size_t r16_smem_bytes(const ktf_frontend* fe) {
   const int LMS = r16_lms(fe->cfg);
   const int out_row = fe->out_dim;
   const int out_sz = (4 * out_row + 3) & ~3;
-  const size_t warp_floats = ((size_t)span_p + 4 * kTile + 4 * LMS + out_sz + 31) & ~(size_t)31;
+  const size_t warp_floats = ((size_t)span_p + 4 * kTile + 4 * LMS + out_sz + 2 + 31) & ~(size_t)31;
   return ((size_t)fe->r16_blob_floats + kR16Warps * warp_floats) * sizeof(float);
 }
 

@@ -25,21 +25,31 @@ __device__ __forceinline__ double block_sum_double(double v, double* scratch) {
   return r;
 }
 
-// One CTA per utterance.
+// One CTA per utterance.  The energy column is strided by the feature dimension in global memory: utterances of up to
+// kVadStage frames copy it into shared memory once (the mean pass), so the 2 * ctx + 1 reads per vote are LDS.
+constexpr int kVadStage = 4096;
+
 __global__ void vad_mask_kernel(const float* __restrict__ feats, int dim, int coeff,
                                 const long long* __restrict__ offs, float thr0, float mean_scale,
                                 float prop_thr, int ctx, float* __restrict__ mask) {
   __shared__ double scratch[32];
+  __shared__ float s_e[kVadStage];
   const long long r0 = offs[blockIdx.x];
   const int T = (int)(offs[blockIdx.x + 1] - r0);
   if (T <= 0) return;
-  const float* e = feats + r0 * dim + coeff;
+  const float* eg = feats + r0 * dim + coeff;
+  const bool staged = T <= kVadStage;
+  auto energy = [&](int t) { return staged ? s_e[t] : eg[(long long)t * dim]; };
 
+  double s = 0.0;                 // vad.py:162-166 -- mean accumulated exactly (fp64), rounded once
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float v = eg[(long long)t * dim];
+    if (staged) s_e[t] = v;
+    s += (double)v;
+  }
+  s = block_sum_double(s, scratch);         // (also the barrier that publishes s_e)
   float thr = thr0;
-  if (mean_scale > 0.0f) {  // vad.py:162-166 -- mean accumulated exactly (fp64), rounded once
-    double s = 0.0;
-    for (int t = threadIdx.x; t < T; t += blockDim.x) s += (double)e[(long long)t * dim];
-    s = block_sum_double(s, scratch);
+  if (mean_scale > 0.0f) {
     const float mean = (float)(s / (double)T);
     thr = thr0 + mean_scale * mean;
   }
@@ -47,20 +57,24 @@ __global__ void vad_mask_kernel(const float* __restrict__ feats, int dim, int co
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     bool keep;
     if (ctx == 0) {
-      keep = e[(long long)t * dim] > thr;                     // vad.py:168-174
+      keep = energy(t) > thr;                                 // vad.py:168-174
     } else {
       float count = 0.0f;                                     // conv1d, SAME zero padding (:180-182)
       for (int k = -ctx; k <= ctx; ++k) {
         const int u = t + k;
-        if (u >= 0 && u < T && e[(long long)u * dim] > thr) count += 1.0f;
+        if (u >= 0 && u < T && energy(u) > thr) count += 1.0f;
       }
       float size = (float)N;                                  // edge window sizes (:124-135,187-193)
-      for (int i = 0; i < ctx; ++i) {                         // left edge: index i, size ctx+1+i
-        if (((i % T) + T) % T == t) size = (float)(ctx + 1 + i);
-      }
-      for (int i = 0; i < ctx; ++i) {                         // right edge: index -ctx+i, size 2ctx-i
-        const int idx = -ctx + i;
-        if ((((idx + T) % T) + T) % T == t) size = (float)(2 * ctx - i);
+      if (t < ctx || t >= T - ctx) {
+        // only the first / last `ctx` frames can be named by the reference's edge lists (python indices i and
+        // -ctx + i, wrapping for utterances shorter than the context); interior frames skip the modulo loops
+        for (int i = 0; i < ctx; ++i) {                       // left edge: index i, size ctx+1+i
+          if (((i % T) + T) % T == t) size = (float)(ctx + 1 + i);
+        }
+        for (int i = 0; i < ctx; ++i) {                       // right edge: index -ctx+i, size 2ctx-i
+          const int idx = -ctx + i;
+          if ((((idx + T) % T) + T) % T == t) size = (float)(2 * ctx - i);
+        }
       }
       keep = __fdiv_rn(count, size) >= prop_thr;              // :197-199
     }
