@@ -90,7 +90,12 @@ struct TcArgs {
   const long long* rows_dev;  // optional: the ACTUAL number of activation rows, read on the device (m_rows, or n_rows
                               // when shift_b); the host value is then only an upper bound (VAD-compacted batches: no
                               // host round trip for the kept-row count)
+  int group_m;              // > 1: grouped tile walk (see tile_coords)
   int tma_store;            // rows are written with TMA tensor stores (tmC is valid; see store_chunk)
+  int l2_stream_out;        // the output is a pure stream much larger than L2 while the operands are re-read by every
+                            // tile (PLDA scoring: 10 GB of scores against 76 MB of vectors): operand loads carry an
+                            // evict-last L2 policy and the boxed stores evict-first, so the stream does not push the
+                            // operands out to HBM (measured without: 3.4-4.3 GB of DRAM reads for 76 MB of inputs)
   int reverse;              // walk the tiles from the last row block to the first (see launch_gemm)
   int debug;                // development knobs (KTF_TC_DEBUG): 1 = skip global stores, 2 = skip the epilogue math
 };
@@ -134,6 +139,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, unsigned long long* bar,
+                                                 int c0, int c1, unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;\n" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+
 // Pulls a contiguous byte range into L2 (no smem, no barrier).  The smem ring holds 4 k-blocks (~1 us of
 // MMA work), less than the HBM latency under load, so the activation rows of a CTA's NEXT tile are
 // requested one whole tile ahead with a single bulk prefetch.
@@ -146,6 +170,12 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
                "cp.async.bulk.commit_group;\n" ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* smem_src, int c0, int c1,
+                                                  unsigned long long policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;\n"
+               "cp.async.bulk.commit_group;\n" ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -229,7 +259,7 @@ template <bool OUT_BF16, bool VEC>
 __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float* vb, float relu_lo, float radd,
                                             unsigned char* stg, int lane, int flags, bool plain, unsigned char* out0,
                                             long long ld_bytes, int cols_left, const CUtensorMap* tmC, int tma_col,
-                                            int tma_row, bool& tma_pending) {
+                                            int tma_row, bool& tma_pending, unsigned long long store_policy) {
   const float4* b4 = reinterpret_cast<const float4*>(vb);
   const float4* s4 = reinterpret_cast<const float4*>(vb + BN);
   const float4* o4 = reinterpret_cast<const float4*>(vb + 2 * BN);
@@ -287,7 +317,10 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
     if (tma) {
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) tma_store_2d(tmC, stg, tma_col + pass * kCols, tma_row);
+      if (lane == 0) {
+        if (store_policy != 0ull) tma_store_2d_hint(tmC, stg, tma_col + pass * kCols, tma_row, store_policy);
+        else tma_store_2d(tmC, stg, tma_col + pass * kCols, tma_row);
+      }
       tma_pending = true;
       continue;
     }
@@ -337,13 +370,22 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
 // Tile walk: row-storing modes go n-fastest (the n-tiles of one row block run on neighbouring CTAs and
 // share the activation rows through L2); STATS goes m-fastest (the unit tiles of one frame block).
 template <int MODE>
-__device__ __forceinline__ void tile_coords(long long tile, long long m_tiles, int n_tiles, int reverse, long long& mt,
-                                            int& nt) {
+__device__ __forceinline__ void tile_coords(long long tile, long long m_tiles, int n_tiles, int reverse, int group_m,
+                                            long long& mt, int& nt) {
   if (reverse) tile = m_tiles * n_tiles - 1 - tile;
   if (MODE == kModeStats) {
     const long long q = tile / m_tiles;
     mt = tile - q * m_tiles;
     nt = (int)q;
+  } else if (group_m > 1) {
+    // grouped walk for wide outputs (PLDA: 196 n-tiles): the 148 CTAs of a wave cover group_m row blocks x ~148 /
+    // group_m column blocks, so a wave re-uses its B tiles group_m times while they are hot and the whole B operand is
+    // swept once per group_m row blocks instead of once per row block (it has to survive in L2 against the output stream)
+    const long long per = (long long)group_m * n_tiles;
+    const long long g = tile / per, r = tile - g * per;
+    const long long m_in = min((long long)group_m, m_tiles - g * group_m);
+    nt = (int)(r / m_in);
+    mt = g * group_m + (r - nt * m_in);
   } else {
     mt = tile / n_tiles;
     nt = (int)(tile - mt * n_tiles);
@@ -411,15 +453,16 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (a.tma_store) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmC) : "memory");
       int stage = 0;
       unsigned phase = 0;
+      const unsigned long long keep = a.l2_stream_out ? l2_policy_evict_last() : 0ull;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         long long mt;
         int nt;
-        tile_coords<MODE>(tile, m_tiles, n_tiles, a.reverse, mt, nt);
+        tile_coords<MODE>(tile, m_tiles, n_tiles, a.reverse, a.group_m, mt, nt);
         const int m0 = (int)(mt * BM), n0 = nt * BN;
         if (a.act_base != nullptr && tile + gridDim.x < total_tiles) {
           long long mt2;
           int nt2;
-          tile_coords<MODE>(tile + gridDim.x, m_tiles, n_tiles, a.reverse, mt2, nt2);
+          tile_coords<MODE>(tile + gridDim.x, m_tiles, n_tiles, a.reverse, a.group_m, mt2, nt2);
           // one CTA per activation row block issues the prefetch (the block is shared by the n- / m-tiles)
           const bool mine = a.shift_b ? (mt2 == 0) : (nt2 == 0);
           if (mine) {
@@ -442,6 +485,9 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (a.shift_b) {
             tma_load_2d(sA + stage * kABytes, &tmA, &full_bar[stage], wcol, m0);
             tma_load_2d(sB + stage * kBBytes, &tmB, &full_bar[stage], d0, n0 + a.ctx[tap]);
+          } else if (keep != 0ull) {
+            tma_load_2d_hint(sA + stage * kABytes, &tmA, &full_bar[stage], d0, m0 + a.ctx[tap], keep);
+            tma_load_2d_hint(sB + stage * kBBytes, &tmB, &full_bar[stage], wcol, n0, keep);
           } else {
             tma_load_2d(sA + stage * kABytes, &tmA, &full_bar[stage], d0, m0 + a.ctx[tap]);
             tma_load_2d(sB + stage * kBBytes, &tmB, &full_bar[stage], wcol, n0);
@@ -490,6 +536,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x - 64;          // 0..255
     int staged_nt0 = -1, staged_nt1 = -1;     // n-tile whose epilogue vectors sit in s_vec[0] / s_vec[1]
     bool tma_pending = false;                 // a TMA store of this warp may still be reading its staging buffer
+    const unsigned long long store_policy = a.l2_stream_out ? l2_policy_evict_first() : 0ull;
     const CUtensorMap* tmc = a.tma_store ? &tmC : nullptr;
     float pre_b = 0.0f, pre_s = 1.0f, pre_o = 0.0f;   // column (nt * BN + et) of bias / scale / offset, prefetched
     int pre_nt = -1;
@@ -507,7 +554,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       long long mt;
       int nt;
-      tile_coords<MODE>(tile, m_tiles, n_tiles, a.reverse, mt, nt);
+      tile_coords<MODE>(tile, m_tiles, n_tiles, a.reverse, a.group_m, mt, nt);
       const int col_base = nt * BN;
       const int acc = it & 1;
       const unsigned acc_phase = (unsigned)(it >> 1) & 1u;
@@ -591,7 +638,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (next < total_tiles) {
             long long mt2;
             int nt2;
-            tile_coords<MODE>(next, m_tiles, n_tiles, a.reverse, mt2, nt2);
+            tile_coords<MODE>(next, m_tiles, n_tiles, a.reverse, a.group_m, mt2, nt2);
             const int have2 = acc ? staged_nt0 : staged_nt1;   // the next tile uses the other accumulator stage
             if (have2 != nt2 && pre_nt != nt2) prefetch_vec(nt2);
           }
@@ -626,10 +673,10 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int trow = (int)(mt * BM) + quarter * 32;
           if (vec_ok && col0 + 32 <= n_cols)
             store_chunk<kBf16, true>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, plain, out0, ld_bytes, 32, tmc,
-                                     col0, trow, tma_pending);
+                                     col0, trow, tma_pending, store_policy);
           else
             store_chunk<kBf16, false>(r[c & 1], vb + cc, relu_lo, radd, stg, lane, flags, false, out0, ld_bytes,
-                                      n_cols - col0, nullptr, 0, 0, tma_pending);
+                                      n_cols - col0, nullptr, 0, 0, tma_pending, 0ull);
         }
       }
       tc_fence_before();
@@ -1427,6 +1474,11 @@ int tc_gemm_nt(const void* A, long long m, long long lda, const void* B, long lo
   args.row_add = row_add;
   args.out = C;
   args.out_ld = ldc;
+  // streaming output (PLDA: the score matrix), operands re-read by every tile: see TcArgs::l2_stream_out
+  args.l2_stream_out = ((double)m * (double)n * (c_bf16 ? 2.0 : 4.0) > 64e6) ? 1 : 0;
+  if (const char* e = getenv("KTF_TC_L2_HINTS")) args.l2_stream_out = atoi(e);
+  args.group_m = (n + BN - 1) / BN > 8 ? 16 : 0;
+  if (const char* e = getenv("KTF_TC_GROUP_M")) args.group_m = atoi(e);
   return c_bf16 ? launch_gemm<kModeBf16>(tmA, tmB, args, st) : launch_gemm<kModeF32>(tmA, tmB, args, st);
 }
 
