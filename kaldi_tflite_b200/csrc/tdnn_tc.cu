@@ -367,6 +367,106 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
   }
 }
 
+// Aligned (VEC) chunk store with TWO staging boxes per warp (pair kernel): the boxed store of pass p may still be
+// reading its box while pass p + 1 fills the other one -- the only wait is for the store issued two passes ago.
+// LEAN: the launch has no per-column scale / offset (PLDA scoring; TDNN layers whose BatchNorm was folded into the weights
+// and the next layer's bias): y = max(acc + bias, lo) (+ row addend) -- one vector instead of three, packed adds.
+template <bool OUT_BF16, bool LEAN>
+__device__ __forceinline__ void store_chunk2(const unsigned (&r)[32], const float* vb, float relu_lo, float radd,
+                                             unsigned char* stg2, int& flip, int lane, int flags, bool plain,
+                                             unsigned char* out0, long long ld_bytes, const CUtensorMap* tmC, int tma_col,
+                                             int tma_row, bool& tma_pending, unsigned long long store_policy) {
+  const float4* b4 = reinterpret_cast<const float4*>(vb);
+  const float4* s4 = reinterpret_cast<const float4*>(vb + BN);
+  const float4* o4 = reinterpret_cast<const float4*>(vb + 2 * BN);
+  constexpr int kCols = kRowSeg / (OUT_BF16 ? 2 : 4);
+  constexpr int kPieces = kRowSeg / 16;
+  constexpr int kGroups = kCols / 8;
+  const int wsw = (lane >> 1) & 3;
+  const bool tma = plain && tmC != nullptr;
+#pragma unroll
+  for (int pass = 0; pass < 32 / kCols; ++pass) {
+    uint4 val[OUT_BF16 ? kGroups : 2 * kGroups];
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      const int c8 = pass * kGroups + g;
+      float x[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 bb = b4[2 * c8 + h];
+        if (LEAN) {
+          // same association as the general form with scale 1 / offset 0, so every path rounds to the same fp32 value
+          x[4 * h + 0] = fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 0]) + bb.x, relu_lo) + radd;
+          x[4 * h + 1] = fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 1]) + bb.y, relu_lo) + radd;
+          x[4 * h + 2] = fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 2]) + bb.z, relu_lo) + radd;
+          x[4 * h + 3] = fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo) + radd;
+        } else {
+          const float4 ss = s4[2 * c8 + h], oo = o4[2 * c8 + h];
+          x[4 * h + 0] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 0]) + bb.x, relu_lo), ss.x, oo.x) + radd;
+          x[4 * h + 1] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 1]) + bb.y, relu_lo), ss.y, oo.y) + radd;
+          x[4 * h + 2] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 2]) + bb.z, relu_lo), ss.z, oo.z) + radd;
+          x[4 * h + 3] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo), ss.w, oo.w) + radd;
+        }
+      }
+      if (OUT_BF16) {
+        val[g] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                            pack_bf16x2(x[6], x[7]));
+      } else {
+        val[2 * g] = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+        val[2 * g + 1] = make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7]));
+      }
+    }
+    unsigned char* stg = stg2 + flip * (32 * kRowSeg);
+    if (tma_pending) {                             // at most one boxed store (the other box) stays in flight
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+      __syncwarp();
+    }
+    uint4* mine = reinterpret_cast<uint4*>(stg + lane * kRowSeg);
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      if (OUT_BF16) {
+        mine[g ^ wsw] = val[g];
+      } else {
+        mine[(2 * g) ^ wsw] = val[2 * g];
+        mine[(2 * g + 1) ^ wsw] = val[2 * g + 1];
+      }
+    }
+    flip ^= 1;
+    if (tma) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (store_policy != 0ull) tma_store_2d_hint(tmC, stg, tma_col + pass * kCols, tma_row, store_policy);
+        else tma_store_2d(tmC, stg, tma_col + pass * kCols, tma_row);
+      }
+      tma_pending = true;
+      continue;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kPieces; ++j) {
+      const int q = j * 32 + lane, rr = q / kPieces, part = q % kPieces;
+      const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kRowSeg + ((part ^ ((rr >> 1) & 3)) * 16));
+      unsigned char* dst = out0 + rr * ld_bytes + pass * kRowSeg + part * 16;
+      if (plain) {
+        *reinterpret_cast<uint4*>(dst) = v;
+        continue;
+      }
+      const int f = __shfl_sync(0xffffffffu, flags, rr);
+      if (f & kRowStore) {
+        *reinterpret_cast<uint4*>(dst) = v;
+        if (f & (kRowFirst | kRowLast)) {
+          const int lo = (f & kRowFirst) ? kHalo : 0, hi = (f & kRowLast) ? kHalo : 0;
+#pragma unroll 1
+          for (int h = -lo; h <= hi; ++h)
+            if (h != 0) *reinterpret_cast<uint4*>(dst + h * ld_bytes) = v;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Tile walk: row-storing modes go n-fastest (the n-tiles of one row block run on neighbouring CTAs and
 // share the activation rows through L2); STATS goes m-fastest (the unit tiles of one frame block).
 template <int MODE>
@@ -690,6 +790,312 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kAccStages * BN));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2) of the row-storing modes: two CTAs of one cluster (the two SMs of a TPC)
+// compute a 256 x 256 tile -- each CTA owns 128 rows of A and of the accumulator and loads only HALF of B (128 of the
+// 256 columns); the MMA, issued by the leader CTA alone, reads both halves.  Per CTA a k-block is 16 KB + 16 KB instead
+// of 16 KB + 32 KB: a third less operand traffic per output tile, and the ring holds kPairStages = 5 k-blocks in 160 KB,
+// which leaves room for double-buffered staging (the boxed store of pass p is still reading its buffer while pass p + 1
+// is being written).
+//   barriers (same offsets in both CTAs): full[s] lives in the LEADER (2 arrivals: each producer; 64 KB of TMA bytes from
+//   both CTAs complete on it), empty[s] and tfull[acc] are signalled in both CTAs by a multicast tcgen05.commit,
+//   tempty[acc] lives in the leader (2 x kEpiWarps arrivals, the peer's epilogue warps arrive through the cluster).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPairStages = 5;
+constexpr int kPairABytes = BM * BK * 2;                 // 16 KB: this CTA's 128 rows
+constexpr int kPairBBytes = (BN / 2) * BK * 2;           // 16 KB: this CTA's 128 of the tile's 256 columns
+constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
+constexpr int kPairStgBytes = kEpiWarps * 2 * 32 * kRowSeg;   // two 32-row x 64-byte boxes per epilogue warp
+constexpr int kSmemPair = kPairStages * kPairStageBytes + 1024 + 256 + kVecBytes + kPairStgBytes + kEpiWarps * 32 * kStgPitch;
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// Remote arrive WITHOUT release semantics: what it orders (TMEM reads before the accumulator is overwritten, the TMA
+// issue order) is covered by tcgen05.fence / the barrier protocol; a cluster-scope release would also wait for the
+// warp's outstanding global stores on every tile.
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are counted on a barrier that may live in the peer CTA (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, unsigned bar_cluster_addr, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                              unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {   // arrives on `bar` in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+          smem_u32(bar)),
+      "h"((unsigned short)3)
+      : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTc, 1)
+tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const TcArgs a) {
+  static_assert(MODE != kModeStats, "the pair kernel covers the row-storing modes");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + kPairStages * kPairABytes;
+  unsigned char* s_stg = smem + kPairStages * kPairStageBytes;          // [kEpiWarps][2][32][kRowSeg] boxes (512 B aligned)
+  unsigned char* s_stg_plain = s_stg + kPairStgBytes;                   // [kEpiWarps][32][kStgPitch] unaligned / ragged path
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_stg_plain + kEpiWarps * 32 * kStgPitch);
+  unsigned long long* full_bar = bars;                        // [kPairStages]   (used in the leader)
+  unsigned long long* empty_bar = bars + kPairStages;         // [kPairStages]
+  unsigned long long* tfull_bar = bars + 2 * kPairStages;     // [kAccStages]
+  unsigned long long* tempty_bar = tfull_bar + kAccStages;    // [kAccStages]    (used in the leader)
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty_bar + kAccStages);
+  float* s_vec = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [kAccStages][3][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster_ctarank();                   // 0 = leader
+  const long long cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  long long m_rows = a.m_rows;
+  const long long n_rows = a.n_rows;
+  if (a.rows_dev != nullptr) m_rows = min(m_rows, *a.rows_dev);
+  constexpr int BM2 = 2 * BM;                                 // rows of a pair tile
+  const long long m_tiles = (m_rows + BM2 - 1) / BM2;
+  const int n_tiles = (int)((n_rows + BN - 1) / BN);
+  const long long total_tiles = m_tiles * n_tiles;
+  const int num_kb = a.num_taps * a.kblocks_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(&full_bar[s], 2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kAccStages * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                        // both CTAs' barriers exist before any remote arrive
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
+      if (a.tma_store) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmC) : "memory");
+      int stage = 0;
+      unsigned phase = 0;
+      for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        long long mt;
+        int nt;
+        tile_coords<MODE>(tile, m_tiles, n_tiles, a.reverse, a.group_m, mt, nt);
+        const int m0 = (int)(mt * BM2) + (int)rank * BM, n0 = nt * BN + (int)rank * (BN / 2);
+        if (a.act_base != nullptr && rank == 0 && tile + num_clusters < total_tiles) {
+          long long mt2;
+          int nt2;
+          tile_coords<MODE>(tile + num_clusters, m_tiles, n_tiles, a.reverse, a.group_m, mt2, nt2);
+          if (nt2 == 0) {                                    // one cluster per row block requests it for all its n-tiles
+            long long r0 = mt2 * BM2 - kHalo, r1 = r0 + BM2 + 2 * kHalo;
+            r0 = r0 < 0 ? 0 : r0;
+            r1 = r1 > m_rows ? m_rows : r1;
+            if (r1 > r0)
+              bulk_prefetch_l2(static_cast<const unsigned char*>(a.act_base) + r0 * a.act_ld_bytes,
+                               (unsigned)((r1 - r0) * a.act_ld_bytes));
+          }
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / a.kblocks_per_tap;
+          const int d0 = (kb - tap * a.kblocks_per_tap) * BK;
+          const int wcol = tap * a.tap_cols + d0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const unsigned full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);   // both CTAs' bytes land on this barrier
+          else mbar_arrive_cluster(full_leader);
+          tma_load_2d_pair(sA + stage * kPairABytes, &tmA, full_leader, d0, m0 + a.ctx[tap]);
+          tma_load_2d_pair(sB + stage * kPairBBytes, &tmB, full_leader, wcol, n0);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (lane == 0 && rank == 0) {
+      const unsigned fmt = a.fp16 ? 0u : 1u;
+      const unsigned idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(BN >> 3) << 17) |
+                             ((unsigned)(BM2 >> 4) << 24);
+      int stage = 0;
+      unsigned phase = 0;
+      int it = 0;
+      for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+        const int acc = it & 1;
+        const unsigned acc_phase = (unsigned)(it >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const unsigned tmem_d = tmem_base + (unsigned)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const unsigned long long adesc = umma_desc(smem_u32(sA + stage * kPairABytes));
+          const unsigned long long bdesc = umma_desc(smem_u32(sB + stage * kPairBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_pair(tmem_d, adesc + (unsigned long long)(2 * k), bdesc + (unsigned long long)(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage]);   // both CTAs' producers may refill the slot
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[acc]);       // both CTAs' epilogues may read their half of the accumulator
+      }
+    }
+  } else {
+    // ================= epilogue warps (2..9), each CTA drains its own 128 rows =================
+    const int quarter = warp & 3;
+    const int colq = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;
+    int staged_nt0 = -1, staged_nt1 = -1;
+    bool tma_pending = false;
+    int stg_flip = 0;                          // which of the warp's two staging boxes the next pass writes
+    const bool lean = a.scale == nullptr && a.offset == nullptr;   // launch-uniform: bias (+ ReLU, + row addend) only
+    const unsigned long long store_policy = a.l2_stream_out ? l2_policy_evict_first() : 0ull;
+    const CUtensorMap* tmc = a.tma_store ? &tmC : nullptr;
+    const unsigned tempty_leader0 = mapa_u32(smem_u32(&tempty_bar[0]), 0), tempty_leader1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+    float pre_b = 0.0f, pre_s = 1.0f, pre_o = 0.0f;
+    int pre_nt = -1;
+    auto prefetch_vec = [&](int nt_) {
+      if (et < BN) {
+        const int col = nt_ * BN + et;
+        const bool ok = col < n_rows;
+        pre_b = (ok && a.bias) ? a.bias[col] : 0.0f;
+        pre_s = (ok && a.scale) ? a.scale[col] : 1.0f;
+        pre_o = (ok && a.offset) ? a.offset[col] : 0.0f;
+      }
+      pre_nt = nt_;
+    };
+    int it = 0;
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+      long long mt;
+      int nt;
+      tile_coords<MODE>(tile, m_tiles, n_tiles, a.reverse, a.group_m, mt, nt);
+      const int col_base = nt * BN;
+      const int acc = it & 1;
+      const unsigned acc_phase = (unsigned)(it >> 1) & 1u;
+      const long long row0 = mt * BM2 + (long long)rank * BM;             // first row of this CTA's half
+      const long long row = row0 + quarter * 32 + lane;
+      const unsigned taddr0 =
+          tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * BN) + (unsigned)(colq * kEpiCols);
+
+      float* vb = s_vec + acc * 3 * BN;
+      const int have_nt = acc ? staged_nt1 : staged_nt0;
+      if (have_nt != nt) {
+        if (pre_nt != nt) prefetch_vec(nt);
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        if (et < BN) {
+          vb[et] = pre_b;
+          vb[BN + et] = pre_s;
+          vb[2 * BN + et] = pre_o;
+        }
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        if (acc) staged_nt1 = nt; else staged_nt0 = nt;
+      }
+      {
+        const long long next = tile + num_clusters;
+        if (next < total_tiles) {
+          long long mt2;
+          int nt2;
+          tile_coords<MODE>(next, m_tiles, n_tiles, a.reverse, a.group_m, mt2, nt2);
+          const int have2 = acc ? staged_nt0 : staged_nt1;
+          if (have2 != nt2 && pre_nt != nt2) prefetch_vec(nt2);
+        }
+      }
+      int flags = 0;
+      if (row < m_rows) flags = a.rowmap ? a.rowmap[row] : kRowStore;
+      if (a.debug & 1) flags = 0;
+      const bool plain = __all_sync(0xffffffffu, flags == kRowStore);
+      float radd = 0.0f;
+      if (a.row_add != nullptr && row < m_rows) radd = a.row_add[row];
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+
+      const int n_cols = (int)n_rows;
+      constexpr bool kBf16 = (MODE == kModeBf16);
+      constexpr int kEs = kBf16 ? 2 : 4;
+      const long long ld_bytes = a.out_ld * kEs;
+      unsigned char* owarp = reinterpret_cast<unsigned char*>(a.out) + (row0 + quarter * 32) * ld_bytes;
+      unsigned char* stg2 = s_stg + (warp - 2) * (2 * 32 * kRowSeg);
+      unsigned char* stg_plain = s_stg_plain + (warp - 2) * (32 * kStgPitch);
+      const bool vec_ok = ((reinterpret_cast<unsigned long long>(a.out) | (unsigned long long)ld_bytes) & 15ull) == 0;
+      const float relu_lo = a.relu ? 0.0f : -3.402823466e+38f;
+      unsigned r[2][32];
+      tmem_ld32_issue(taddr0, r[0]);
+#pragma unroll
+      for (int c = 0; c < kEpiChunks; ++c) {
+        tmem_ld_wait(r[c & 1]);
+        if (c + 1 < kEpiChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) & 1]);
+        const int cc = colq * kEpiCols + c * 32;
+        const int col0 = col_base + cc;
+        if (col0 >= n_cols || (a.debug & 2)) continue;
+        unsigned char* out0 = owarp + (long long)col0 * kEs;
+        const int trow = (int)row0 + quarter * 32;
+        if (vec_ok && col0 + 32 <= n_cols) {
+          if (lean)
+            store_chunk2<kBf16, true>(r[c & 1], vb + cc, relu_lo, radd, stg2, stg_flip, lane, flags, plain, out0,
+                                      ld_bytes, tmc, col0, trow, tma_pending, store_policy);
+          else
+            store_chunk2<kBf16, false>(r[c & 1], vb + cc, relu_lo, radd, stg2, stg_flip, lane, flags, plain, out0,
+                                       ld_bytes, tmc, col0, trow, tma_pending, store_policy);
+        } else
+          store_chunk<kBf16, false>(r[c & 1], vb + cc, relu_lo, radd, stg_plain, lane, flags, false, out0, ld_bytes,
+                                    n_cols - col0, nullptr, 0, 0, tma_pending, 0ull);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // smem outlives the last boxes
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // the peer's MMAs / remote arrivals are done with this CTA's smem
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kAccStages * BN));
   }
 }
 
@@ -1270,6 +1676,71 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& ar
   return KTF_OK;
 }
 
+int pair_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("KTF_TC_PAIR");     // development knob: 0 = single-CTA tiles for every launch
+    on = e ? atoi(e) : 1;
+  }
+  return on;
+}
+
+// CTA-pair launch of a row-storing mode.  tmB must be encoded with 128-row boxes (each CTA loads half of the tile's 256
+// columns); everything else as launch_gemm.
+template <int MODE>
+int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const TcArgs& args_in, cudaStream_t st) {
+  TcArgs args = args_in;
+  CUtensorMap tmC = tmA;
+  args.tma_store = 0;
+  if (tma_store_enabled() && args.out != nullptr) {
+    const int es = (MODE == kModeBf16) ? 2 : 4;
+    if (encode_map_out(&tmC, args.out, es, (unsigned long long)args.n_rows, (unsigned long long)args.m_rows,
+                       (unsigned long long)args.out_ld))
+      args.tma_store = 1;
+  }
+  static unsigned long long attr_done = 0;
+  if (ktf::first_use_on_device(&attr_done))
+    KTF_CUDA(cudaFuncSetAttribute(tdnn_tc_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPair));
+  const long long tiles = ((args.m_rows + 2 * BM - 1) / (2 * BM)) * ((args.n_rows + BN - 1) / BN);
+  if (tiles <= 0) return KTF_OK;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("KTF_TC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  args.debug = dbg;
+  // clusters that can be co-resident (a TPC with one SM fused off cannot host a pair): a persistent grid larger than
+  // that would run its last clusters as a second wave
+  static int max_clusters[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (max_clusters[dev] == 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)ktf::num_sms() & ~1u);
+    cfg.blockDim = dim3(kThreadsTc);
+    cfg.dynamicSmemBytes = kSmemPair;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, tdnn_tc_pair_kernel<MODE>, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = ktf::num_sms() / 2;
+    }
+    max_clusters[dev] = n;
+    if (getenv("KTF_TC_DEBUG_OCC")) fprintf(stderr, "[ktf] pair kernel: %d co-resident clusters on %d SMs\n", n, ktf::num_sms());
+  }
+  const unsigned clusters = (unsigned)std::min<long long>(tiles, std::min(max_clusters[dev], ktf::num_sms() / 2));
+  tdnn_tc_pair_kernel<MODE><<<2 * clusters, kThreadsTc, kSmemPair, st>>>(tmA, tmB_half, tmC, args);
+  KTF_LAUNCH_OK();
+  return KTF_OK;
+}
+
 void fill_taps(TcArgs& args, const TcLayer& L, bool a_is_spliced, long long a_cols) {
   if (a_is_spliced) {
     args.num_taps = 1;
@@ -1308,6 +1779,8 @@ int run_layer(const TcLayer& L, const ktf_affine* a, const __nv_bfloat16* A, lon
   args.relu = a->cfg.activation == KTF_ACT_RELU;
   args.out = out;
   args.out_ld = out_ld;
+  if (pair_enabled())   // CTA-pair tiles: each CTA loads 128 of the 256 weight rows of a tile (tmW_m has 128-row boxes)
+    return out_bf16 ? launch_gemm_pair<kModeBf16>(tmA, L.tmW_m, args, st) : launch_gemm_pair<kModeF32>(tmA, L.tmW_m, args, st);
   return out_bf16 ? launch_gemm<kModeBf16>(tmA, L.tmW_n, args, st) : launch_gemm<kModeF32>(tmA, L.tmW_n, args, st);
 }
 
@@ -1479,6 +1952,12 @@ int tc_gemm_nt(const void* A, long long m, long long lda, const void* B, long lo
   if (const char* e = getenv("KTF_TC_L2_HINTS")) args.l2_stream_out = atoi(e);
   args.group_m = (n + BN - 1) / BN > 8 ? 16 : 0;
   if (const char* e = getenv("KTF_TC_GROUP_M")) args.group_m = atoi(e);
+  if (pair_enabled()) {
+    CUtensorMap tmBh;
+    if ((rc = encode_map(&tmBh, B, (unsigned long long)K, (unsigned long long)n, (unsigned long long)ldb, BK, BN / 2)) != KTF_OK)
+      return rc;
+    return c_bf16 ? launch_gemm_pair<kModeBf16>(tmA, tmBh, args, st) : launch_gemm_pair<kModeF32>(tmA, tmBh, args, st);
+  }
   return c_bf16 ? launch_gemm<kModeBf16>(tmA, tmB, args, st) : launch_gemm<kModeF32>(tmA, tmB, args, st);
 }
 
