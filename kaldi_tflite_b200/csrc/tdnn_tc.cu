@@ -371,14 +371,14 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
 // reading its box while pass p + 1 fills the other one -- the only wait is for the store issued two passes ago.
 // LEAN: the launch has no per-column scale / offset (PLDA scoring; TDNN layers whose BatchNorm was folded into the weights
 // and the next layer's bias): y = max(acc + bias, lo) (+ row addend) -- one vector instead of three, packed adds.
-template <bool OUT_BF16, bool LEAN>
+template <bool OUT_BF16, bool LEAN, int VSTRIDE>
 __device__ __forceinline__ void store_chunk2(const unsigned (&r)[32], const float* vb, float relu_lo, float radd,
                                              unsigned char* stg2, int& flip, int lane, int flags, bool plain,
                                              unsigned char* out0, long long ld_bytes, const CUtensorMap* tmC, int tma_col,
                                              int tma_row, bool& tma_pending, unsigned long long store_policy) {
   const float4* b4 = reinterpret_cast<const float4*>(vb);
-  const float4* s4 = reinterpret_cast<const float4*>(vb + BN);
-  const float4* o4 = reinterpret_cast<const float4*>(vb + 2 * BN);
+  const float4* s4 = reinterpret_cast<const float4*>(vb + VSTRIDE);
+  const float4* o4 = reinterpret_cast<const float4*>(vb + 2 * VSTRIDE);
   constexpr int kCols = kRowSeg / (OUT_BF16 ? 2 : 4);
   constexpr int kPieces = kRowSeg / 16;
   constexpr int kGroups = kCols / 8;
@@ -467,28 +467,72 @@ __device__ __forceinline__ void store_chunk2(const unsigned (&r)[32], const floa
   }
 }
 
+// Ragged / unaligned chunk of the pair kernel (right edge of the matrix, output pitch not a multiple of 16 bytes): fp32
+// staging, bounds-checked scalar stores with the per-row flags.  Same arithmetic (and association) as store_chunk2.
+template <bool OUT_BF16, int VSTRIDE>
+__device__ __forceinline__ void store_chunk_ragged(const unsigned (&r)[32], const float* vb, bool lean, float relu_lo,
+                                                   float radd, unsigned char* stg, int lane, int flags, unsigned char* out0,
+                                                   long long ld_bytes, int cols_left) {
+  constexpr int kCols = 16;                              // columns per pass (kStgPitch = 80 bytes holds 16 floats + pad)
+  constexpr int kEs = OUT_BF16 ? 2 : 4;
+#pragma unroll      // (compile-time indices into r[]: a rolled loop would push the accumulator registers to local memory)
+  for (int pass = 0; pass < 32 / kCols; ++pass) {
+    float* mine = reinterpret_cast<float*>(stg + lane * kStgPitch);
+#pragma unroll
+    for (int i = 0; i < kCols; ++i) {
+      const int c = pass * kCols + i;
+      const float b = vb[c], sc = lean ? 1.0f : vb[VSTRIDE + c], of = lean ? 0.0f : vb[2 * VSTRIDE + c];
+      const float t = fmaxf(__uint_as_float(r[c]) + b, relu_lo);
+      mine[i] = (lean ? t : fmaf(t, sc, of)) + radd;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int k = lane; k < 32 * kCols; k += 32) {
+      const int rr = k / kCols, col = k % kCols;
+      const float v = *reinterpret_cast<const float*>(stg + rr * kStgPitch + col * 4);
+      const int f = __shfl_sync(0xffffffffu, flags, rr);
+      if ((f & kRowStore) && pass * kCols + col < cols_left) {
+        const int lo = (f & kRowFirst) ? kHalo : 0, hi = (f & kRowLast) ? kHalo : 0;
+        unsigned char* dst = out0 + rr * ld_bytes + (long long)(pass * kCols + col) * kEs;
+#pragma unroll 1
+        for (int h = -lo; h <= hi; ++h) {
+          if (OUT_BF16) *reinterpret_cast<__nv_bfloat16*>(dst + h * ld_bytes) = __float2bfloat16_rn(v);
+          else *reinterpret_cast<float*>(dst + h * ld_bytes) = v;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Tile walk: row-storing modes go n-fastest (the n-tiles of one row block run on neighbouring CTAs and
 // share the activation rows through L2); STATS goes m-fastest (the unit tiles of one frame block).
 template <int MODE>
-__device__ __forceinline__ void tile_coords(long long tile, long long m_tiles, int n_tiles, int reverse, int group_m,
+__device__ __forceinline__ void tile_coords(long long tile64, long long m_tiles64, int n_tiles, int reverse, int group_m,
                                             long long& mt, int& nt) {
-  if (reverse) tile = m_tiles * n_tiles - 1 - tile;
+  // tile counts fit 32 bits (2^31 tiles of 128 x 256 outputs is 10^14 elements): 32-bit divisions, not 64-bit ones --
+  // every epilogue thread runs this twice per tile
+  const unsigned m_tiles = (unsigned)m_tiles64, nt_n = (unsigned)n_tiles;
+  unsigned tile = (unsigned)tile64;
+  if (reverse) tile = m_tiles * nt_n - 1u - tile;
   if (MODE == kModeStats) {
-    const long long q = tile / m_tiles;
+    const unsigned q = tile / m_tiles;
     mt = tile - q * m_tiles;
     nt = (int)q;
   } else if (group_m > 1) {
     // grouped walk for wide outputs (PLDA: 196 n-tiles): the 148 CTAs of a wave cover group_m row blocks x ~148 /
     // group_m column blocks, so a wave re-uses its B tiles group_m times while they are hot and the whole B operand is
     // swept once per group_m row blocks instead of once per row block (it has to survive in L2 against the output stream)
-    const long long per = (long long)group_m * n_tiles;
-    const long long g = tile / per, r = tile - g * per;
-    const long long m_in = min((long long)group_m, m_tiles - g * group_m);
-    nt = (int)(r / m_in);
-    mt = g * group_m + (r - nt * m_in);
+    const unsigned per = (unsigned)group_m * nt_n;
+    const unsigned g = tile / per, r = tile - g * per;
+    const unsigned m_in = min((unsigned)group_m, m_tiles - g * (unsigned)group_m);
+    const unsigned q = r / m_in;
+    nt = (int)q;
+    mt = g * (unsigned)group_m + (r - q * m_in);
   } else {
-    mt = tile / n_tiles;
-    nt = (int)(tile - mt * n_tiles);
+    const unsigned q = tile / nt_n;
+    mt = q;
+    nt = (int)(tile - q * nt_n);
   }
 }
 
@@ -809,7 +853,8 @@ constexpr int kPairABytes = BM * BK * 2;                 // 16 KB: this CTA's 12
 constexpr int kPairBBytes = (BN / 2) * BK * 2;           // 16 KB: this CTA's 128 of the tile's 256 columns
 constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
 constexpr int kPairStgBytes = kEpiWarps * 2 * 32 * kRowSeg;   // two 32-row x 64-byte boxes per epilogue warp
-constexpr int kSmemPair = kPairStages * kPairStageBytes + 1024 + 256 + kVecBytes + kPairStgBytes + kEpiWarps * 32 * kStgPitch;
+constexpr int kPairVecBytes = kEpiWarps * 3 * kEpiCols * 4;   // per-warp [bias | scale | offset] of the warp's 128 columns
+constexpr int kSmemPair = kPairStages * kPairStageBytes + 1024 + 256 + kPairVecBytes + kPairStgBytes + kEpiWarps * 32 * kStgPitch;
 
 __device__ __forceinline__ unsigned cluster_ctarank() {
   unsigned r;
@@ -875,7 +920,7 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   unsigned long long* tfull_bar = bars + 2 * kPairStages;     // [kAccStages]
   unsigned long long* tempty_bar = tfull_bar + kAccStages;    // [kAccStages]    (used in the leader)
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty_bar + kAccStages);
-  float* s_vec = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [kAccStages][3][BN]
+  float* s_vec = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [kEpiWarps][3][kEpiCols]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned rank = cluster_ctarank();                   // 0 = leader
@@ -986,22 +1031,33 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;
     const int colq = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;
-    int staged_nt0 = -1, staged_nt1 = -1;
     bool tma_pending = false;
     int stg_flip = 0;                          // which of the warp's two staging boxes the next pass writes
     const bool lean = a.scale == nullptr && a.offset == nullptr;   // launch-uniform: bias (+ ReLU, + row addend) only
     const unsigned long long store_policy = a.l2_stream_out ? l2_policy_evict_first() : 0ull;
     const CUtensorMap* tmc = a.tma_store ? &tmC : nullptr;
     const unsigned tempty_leader0 = mapa_u32(smem_u32(&tempty_bar[0]), 0), tempty_leader1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
-    float pre_b = 0.0f, pre_s = 1.0f, pre_o = 0.0f;
-    int pre_nt = -1;
+    // Per-column vectors of the warp's 128 columns live in a region PRIVATE to the warp (no CTA-wide barrier when the
+    // n-tile changes -- in PLDA scoring it changes on every tile): lane l owns columns 4l .. 4l+3, the next tile's values
+    // are loaded into registers one tile ahead.
+    float* wv = s_vec + (warp - 2) * (3 * kEpiCols);
+    int wv_nt = -1, pre_nt = -1;
+    float4 pre_b = make_float4(0.f, 0.f, 0.f, 0.f), pre_s = make_float4(1.f, 1.f, 1.f, 1.f), pre_o = pre_b;
+    auto load4 = [&](const float* p, int col, float fill) {
+      if (p == nullptr) return make_float4(fill, fill, fill, fill);
+      if (col + 3 < n_rows) return *reinterpret_cast<const float4*>(p + col);     // cudaMalloc'ed vectors, col % 4 == 0
+      float4 v = make_float4(fill, fill, fill, fill);
+      if (col < n_rows) v.x = p[col];
+      if (col + 1 < n_rows) v.y = p[col + 1];
+      if (col + 2 < n_rows) v.z = p[col + 2];
+      return v;
+    };
     auto prefetch_vec = [&](int nt_) {
-      if (et < BN) {
-        const int col = nt_ * BN + et;
-        const bool ok = col < n_rows;
-        pre_b = (ok && a.bias) ? a.bias[col] : 0.0f;
-        pre_s = (ok && a.scale) ? a.scale[col] : 1.0f;
-        pre_o = (ok && a.offset) ? a.offset[col] : 0.0f;
+      const int col = nt_ * BN + colq * kEpiCols + 4 * lane;
+      pre_b = load4(a.bias, col, 0.0f);
+      if (!lean) {
+        pre_s = load4(a.scale, col, 1.0f);
+        pre_o = load4(a.offset, col, 0.0f);
       }
       pre_nt = nt_;
     };
@@ -1018,18 +1074,16 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const unsigned taddr0 =
           tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * BN) + (unsigned)(colq * kEpiCols);
 
-      float* vb = s_vec + acc * 3 * BN;
-      const int have_nt = acc ? staged_nt1 : staged_nt0;
-      if (have_nt != nt) {
+      if (wv_nt != nt) {
         if (pre_nt != nt) prefetch_vec(nt);
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
-        if (et < BN) {
-          vb[et] = pre_b;
-          vb[BN + et] = pre_s;
-          vb[2 * BN + et] = pre_o;
+        __syncwarp();                            // every lane is done reading the previous tile's vectors
+        reinterpret_cast<float4*>(wv)[lane] = pre_b;
+        if (!lean) {
+          reinterpret_cast<float4*>(wv + kEpiCols)[lane] = pre_s;
+          reinterpret_cast<float4*>(wv + 2 * kEpiCols)[lane] = pre_o;
         }
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
-        if (acc) staged_nt1 = nt; else staged_nt0 = nt;
+        __syncwarp();
+        wv_nt = nt;
       }
       {
         const long long next = tile + num_clusters;
@@ -1037,8 +1091,7 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           long long mt2;
           int nt2;
           tile_coords<MODE>(next, m_tiles, n_tiles, a.reverse, a.group_m, mt2, nt2);
-          const int have2 = acc ? staged_nt0 : staged_nt1;
-          if (have2 != nt2 && pre_nt != nt2) prefetch_vec(nt2);
+          if (nt2 != nt && pre_nt != nt2) prefetch_vec(nt2);
         }
       }
       int flags = 0;
@@ -1072,14 +1125,20 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int trow = (int)row0 + quarter * 32;
         if (vec_ok && col0 + 32 <= n_cols) {
           if (lean)
-            store_chunk2<kBf16, true>(r[c & 1], vb + cc, relu_lo, radd, stg2, stg_flip, lane, flags, plain, out0,
-                                      ld_bytes, tmc, col0, trow, tma_pending, store_policy);
+            store_chunk2<kBf16, true, kEpiCols>(r[c & 1], wv + c * 32, relu_lo, radd, stg2, stg_flip, lane, flags, plain,
+                                                out0, ld_bytes, tmc, col0, trow, tma_pending, store_policy);
           else
-            store_chunk2<kBf16, false>(r[c & 1], vb + cc, relu_lo, radd, stg2, stg_flip, lane, flags, plain, out0,
-                                       ld_bytes, tmc, col0, trow, tma_pending, store_policy);
-        } else
-          store_chunk<kBf16, false>(r[c & 1], vb + cc, relu_lo, radd, stg_plain, lane, flags, false, out0, ld_bytes,
-                                    n_cols - col0, nullptr, 0, 0, tma_pending, 0ull);
+            store_chunk2<kBf16, false, kEpiCols>(r[c & 1], wv + c * 32, relu_lo, radd, stg2, stg_flip, lane, flags, plain,
+                                                 out0, ld_bytes, tmc, col0, trow, tma_pending, store_policy);
+        } else {
+          if (tma_pending) {                     // the ragged path reads back with the generic proxy: no box in flight
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            __syncwarp();
+            tma_pending = false;
+          }
+          store_chunk_ragged<kBf16, kEpiCols>(r[c & 1], wv + c * 32, lean, relu_lo, radd, stg_plain, lane, flags, out0,
+                                              ld_bytes, n_cols - col0);
+        }
       }
       tc_fence_before();
       __syncwarp();
