@@ -848,13 +848,23 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   both CTAs complete on it), empty[s] and tfull[acc] are signalled in both CTAs by a multicast tcgen05.commit,
 //   tempty[acc] lives in the leader (2 x kEpiWarps arrivals, the peer's epilogue warps arrive through the cluster).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kPairStages = 5;
 constexpr int kPairABytes = BM * BK * 2;                 // 16 KB: this CTA's 128 rows
 constexpr int kPairBBytes = (BN / 2) * BK * 2;           // 16 KB: this CTA's 128 of the tile's 256 columns
 constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
-constexpr int kPairStgBytes = kEpiWarps * 2 * 32 * kRowSeg;   // two 32-row x 64-byte boxes per epilogue warp
-constexpr int kPairVecBytes = kEpiWarps * 3 * kEpiCols * 4;   // per-warp [bias | scale | offset] of the warp's 128 columns
-constexpr int kSmemPair = kPairStages * kPairStageBytes + 1024 + 256 + kPairVecBytes + kPairStgBytes + kEpiWarps * 32 * kStgPitch;
+// EW epilogue warps per CTA (8 or 16: EW / 4 warps share a TMEM lane quarter and split the tile's 256 columns).  The
+// epilogue of the short-K layers and of PLDA scoring is latency-bound (a thread owns one accumulator row and walks
+// TMEM load -> per-column vectors -> staging -> boxed store); 16 warps double the chains in flight.  They pay for it
+// with one ring stage (4 x 32 KB instead of 5) and 112 registers per thread.
+template <int EW> struct PairCfg {
+  static constexpr int kStages = EW == 16 ? 4 : 5;
+  static constexpr int kThreads = 64 + EW * 32;
+  static constexpr int kCols = BN / (EW / 4);              // tile columns per epilogue warp: 128 or 64
+  static constexpr int kChunks = kCols / 32;
+  static constexpr int kStgBytes = EW * 2 * 32 * kRowSeg;  // two 32-row x 64-byte boxes per epilogue warp
+  static constexpr int kVecBytes = EW * 3 * kCols * 4;     // per-warp [bias | scale | offset] of the warp's columns
+  static constexpr int kSmem = kStages * kPairStageBytes + 1024 + 256 + kVecBytes + kStgBytes;
+};
+static_assert(PairCfg<8>::kSmem <= 227 * 1024 && PairCfg<16>::kSmem <= 227 * 1024, "pair kernel shared memory");
 
 __device__ __forceinline__ unsigned cluster_ctarank() {
   unsigned r;
@@ -903,24 +913,26 @@ __device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {   //
       : "memory");
 }
 
-template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTc, 1)
+template <int MODE, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<EW>::kThreads, 1)
 tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const TcArgs a) {
   static_assert(MODE != kModeStats, "the pair kernel covers the row-storing modes");
+  using Cfg = PairCfg<EW>;
+  constexpr int kPairStages = Cfg::kStages;
+  constexpr int kPCols = Cfg::kCols, kPChunks = Cfg::kChunks;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + kPairStages * kPairABytes;
-  unsigned char* s_stg = smem + kPairStages * kPairStageBytes;          // [kEpiWarps][2][32][kRowSeg] boxes (512 B aligned)
-  unsigned char* s_stg_plain = s_stg + kPairStgBytes;                   // [kEpiWarps][32][kStgPitch] unaligned / ragged path
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_stg_plain + kEpiWarps * 32 * kStgPitch);
+  unsigned char* s_stg = smem + kPairStages * kPairStageBytes;          // [EW][2][32][kRowSeg] boxes (512 B aligned)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_stg + Cfg::kStgBytes);
   unsigned long long* full_bar = bars;                        // [kPairStages]   (used in the leader)
   unsigned long long* empty_bar = bars + kPairStages;         // [kPairStages]
   unsigned long long* tfull_bar = bars + 2 * kPairStages;     // [kAccStages]
   unsigned long long* tempty_bar = tfull_bar + kAccStages;    // [kAccStages]    (used in the leader)
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty_bar + kAccStages);
-  float* s_vec = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [kEpiWarps][3][kEpiCols]
+  float* s_vec = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // [EW][3][kPCols]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned rank = cluster_ctarank();                   // 0 = leader
@@ -941,7 +953,7 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 2 * kEpiWarps);
+      mbar_init(&tempty_bar[s], 2 * EW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -1027,10 +1039,9 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ================= epilogue warps (2..9), each CTA drains its own 128 rows =================
+    // ================= epilogue warps (2 .. EW + 1), each CTA drains its own 128 rows =================
     const int quarter = warp & 3;
     const int colq = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;
     bool tma_pending = false;
     int stg_flip = 0;                          // which of the warp's two staging boxes the next pass writes
     const bool lean = a.scale == nullptr && a.offset == nullptr;   // launch-uniform: bias (+ ReLU, + row addend) only
@@ -1040,24 +1051,22 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Per-column vectors of the warp's 128 columns live in a region PRIVATE to the warp (no CTA-wide barrier when the
     // n-tile changes -- in PLDA scoring it changes on every tile): lane l owns columns 4l .. 4l+3, the next tile's values
     // are loaded into registers one tile ahead.
-    float* wv = s_vec + (warp - 2) * (3 * kEpiCols);
+    float* wv = s_vec + (warp - 2) * (3 * kPCols);
+    constexpr int kVW = kPCols / 32;           // columns per lane: 4 (EW = 8) or 2 (EW = 16)
     int wv_nt = -1, pre_nt = -1;
-    float4 pre_b = make_float4(0.f, 0.f, 0.f, 0.f), pre_s = make_float4(1.f, 1.f, 1.f, 1.f), pre_o = pre_b;
-    auto load4 = [&](const float* p, int col, float fill) {
-      if (p == nullptr) return make_float4(fill, fill, fill, fill);
-      if (col + 3 < n_rows) return *reinterpret_cast<const float4*>(p + col);     // cudaMalloc'ed vectors, col % 4 == 0
-      float4 v = make_float4(fill, fill, fill, fill);
-      if (col < n_rows) v.x = p[col];
-      if (col + 1 < n_rows) v.y = p[col + 1];
-      if (col + 2 < n_rows) v.z = p[col + 2];
-      return v;
-    };
+    float pre_b[kVW], pre_s[kVW], pre_o[kVW];
+#pragma unroll
+    for (int u = 0; u < kVW; ++u) { pre_b[u] = 0.0f; pre_s[u] = 1.0f; pre_o[u] = 0.0f; }
     auto prefetch_vec = [&](int nt_) {
-      const int col = nt_ * BN + colq * kEpiCols + 4 * lane;
-      pre_b = load4(a.bias, col, 0.0f);
-      if (!lean) {
-        pre_s = load4(a.scale, col, 1.0f);
-        pre_o = load4(a.offset, col, 0.0f);
+      const int col = nt_ * BN + colq * kPCols + kVW * lane;
+#pragma unroll
+      for (int u = 0; u < kVW; ++u) {
+        const bool ok = col + u < n_rows;
+        pre_b[u] = (ok && a.bias) ? a.bias[col + u] : 0.0f;
+        if (!lean) {
+          pre_s[u] = (ok && a.scale) ? a.scale[col + u] : 1.0f;
+          pre_o[u] = (ok && a.offset) ? a.offset[col + u] : 0.0f;
+        }
       }
       pre_nt = nt_;
     };
@@ -1072,15 +1081,18 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const long long row0 = mt * BM2 + (long long)rank * BM;             // first row of this CTA's half
       const long long row = row0 + quarter * 32 + lane;
       const unsigned taddr0 =
-          tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * BN) + (unsigned)(colq * kEpiCols);
+          tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * BN) + (unsigned)(colq * kPCols);
 
       if (wv_nt != nt) {
         if (pre_nt != nt) prefetch_vec(nt);
         __syncwarp();                            // every lane is done reading the previous tile's vectors
-        reinterpret_cast<float4*>(wv)[lane] = pre_b;
-        if (!lean) {
-          reinterpret_cast<float4*>(wv + kEpiCols)[lane] = pre_s;
-          reinterpret_cast<float4*>(wv + 2 * kEpiCols)[lane] = pre_o;
+#pragma unroll
+        for (int u = 0; u < kVW; ++u) {
+          wv[kVW * lane + u] = pre_b[u];
+          if (!lean) {
+            wv[kPCols + kVW * lane + u] = pre_s[u];
+            wv[2 * kPCols + kVW * lane + u] = pre_o[u];
+          }
         }
         __syncwarp();
         wv_nt = nt;
@@ -1109,26 +1121,31 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const long long ld_bytes = a.out_ld * kEs;
       unsigned char* owarp = reinterpret_cast<unsigned char*>(a.out) + (row0 + quarter * 32) * ld_bytes;
       unsigned char* stg2 = s_stg + (warp - 2) * (2 * 32 * kRowSeg);
-      unsigned char* stg_plain = s_stg_plain + (warp - 2) * (32 * kStgPitch);
       const bool vec_ok = ((reinterpret_cast<unsigned long long>(a.out) | (unsigned long long)ld_bytes) & 15ull) == 0;
       const float relu_lo = a.relu ? 0.0f : -3.402823466e+38f;
-      unsigned r[2][32];
+      // EW = 8: TMEM loads run one chunk ahead of the math (two register buffers); EW = 16 has the warps to cover the
+      // load latency and 96 registers per thread: one buffer
+      constexpr int kRB = EW == 16 ? 1 : 2;
+      unsigned r[kRB][32];
       tmem_ld32_issue(taddr0, r[0]);
 #pragma unroll
-      for (int c = 0; c < kEpiChunks; ++c) {
-        tmem_ld_wait(r[c & 1]);
-        if (c + 1 < kEpiChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) & 1]);
-        const int cc = colq * kEpiCols + c * 32;
+      for (int c = 0; c < kPChunks; ++c) {
+        tmem_ld_wait(r[c % kRB]);
+        if (kRB == 2 && c + 1 < kPChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) % kRB]);
+        const int cc = colq * kPCols + c * 32;
         const int col0 = col_base + cc;
-        if (col0 >= n_cols || (a.debug & 2)) continue;
+        if (col0 >= n_cols || (a.debug & 2)) {
+          if (kRB == 1 && c + 1 < kPChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[0]);
+          continue;
+        }
         unsigned char* out0 = owarp + (long long)col0 * kEs;
         const int trow = (int)row0 + quarter * 32;
         if (vec_ok && col0 + 32 <= n_cols) {
           if (lean)
-            store_chunk2<kBf16, true, kEpiCols>(r[c & 1], wv + c * 32, relu_lo, radd, stg2, stg_flip, lane, flags, plain,
+            store_chunk2<kBf16, true, kPCols>(r[c % kRB], wv + c * 32, relu_lo, radd, stg2, stg_flip, lane, flags, plain,
                                                 out0, ld_bytes, tmc, col0, trow, tma_pending, store_policy);
           else
-            store_chunk2<kBf16, false, kEpiCols>(r[c & 1], wv + c * 32, relu_lo, radd, stg2, stg_flip, lane, flags, plain,
+            store_chunk2<kBf16, false, kPCols>(r[c % kRB], wv + c * 32, relu_lo, radd, stg2, stg_flip, lane, flags, plain,
                                                  out0, ld_bytes, tmc, col0, trow, tma_pending, store_policy);
         } else {
           if (tma_pending) {                     // the ragged path reads back with the generic proxy: no box in flight
@@ -1136,9 +1153,11 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             tma_pending = false;
           }
-          store_chunk_ragged<kBf16, kEpiCols>(r[c & 1], wv + c * 32, lean, relu_lo, radd, stg_plain, lane, flags, out0,
-                                              ld_bytes, n_cols - col0);
+          // (the warp's two boxes, 4 KB, serve as the fp32 staging of the ragged path)
+          store_chunk_ragged<kBf16, kPCols>(r[c % kRB], wv + c * 32, lean, relu_lo, radd, stg2, lane, flags, out0, ld_bytes,
+                                            n_cols - col0);
         }
+        if (kRB == 1 && c + 1 < kPChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[0]);
       }
       tc_fence_before();
       __syncwarp();
@@ -1746,8 +1765,32 @@ int pair_enabled() {
 
 // CTA-pair launch of a row-storing mode.  tmB must be encoded with 128-row boxes (each CTA loads half of the tile's 256
 // columns); everything else as launch_gemm.
+// Epilogue warps per CTA of the pair kernel.  Measured (config 3 / wav2xvec / PLDA 50 000^2): 16 warps win for bf16 rows
+// (0.798 vs 0.834 ms, 4.62 vs 4.79 ms), 8 warps for fp32 rows (2.61 vs 2.73 ms: two staging passes per chunk and 96
+// registers do not mix).  KTF_TC_PAIR_EPI_WARPS overrides both.
+int pair_epi_warps(bool bf16_rows) {
+  static int ew = -1;
+  if (ew < 0) {
+    const char* e = getenv("KTF_TC_PAIR_EPI_WARPS");
+    ew = e ? atoi(e) : 0;
+  }
+  if (ew == 8 || ew == 16) return ew;
+  return bf16_rows ? 16 : 8;
+}
+
+template <int MODE, int EW>
+int launch_gemm_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const TcArgs& args_in, cudaStream_t st);
+
 template <int MODE>
 int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const TcArgs& args_in, cudaStream_t st) {
+  return pair_epi_warps(MODE == kModeBf16) == 16 ? launch_gemm_pair_ew<MODE, 16>(tmA, tmB_half, args_in, st)
+                                : launch_gemm_pair_ew<MODE, 8>(tmA, tmB_half, args_in, st);
+}
+
+template <int MODE, int EW>
+int launch_gemm_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const TcArgs& args_in, cudaStream_t st) {
+  constexpr int kSmemPair = PairCfg<EW>::kSmem;
+  constexpr int kPairThreads = PairCfg<EW>::kThreads;
   TcArgs args = args_in;
   CUtensorMap tmC = tmA;
   args.tma_store = 0;
@@ -1759,7 +1802,7 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const 
   }
   static unsigned long long attr_done = 0;
   if (ktf::first_use_on_device(&attr_done))
-    KTF_CUDA(cudaFuncSetAttribute(tdnn_tc_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPair));
+    KTF_CUDA(cudaFuncSetAttribute(tdnn_tc_pair_kernel<MODE, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPair));
   const long long tiles = ((args.m_rows + 2 * BM - 1) / (2 * BM)) * ((args.n_rows + BN - 1) / BN);
   if (tiles <= 0) return KTF_OK;
   static int dbg = -1;
@@ -1777,7 +1820,7 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const 
   if (max_clusters[dev] == 0) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)ktf::num_sms() & ~1u);
-    cfg.blockDim = dim3(kThreadsTc);
+    cfg.blockDim = dim3(kPairThreads);
     cfg.dynamicSmemBytes = kSmemPair;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1787,7 +1830,7 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const 
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, tdnn_tc_pair_kernel<MODE>, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, tdnn_tc_pair_kernel<MODE, EW>, &cfg) != cudaSuccess || n <= 0) {
       (void)cudaGetLastError();
       n = ktf::num_sms() / 2;
     }
@@ -1795,7 +1838,7 @@ int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const 
     if (getenv("KTF_TC_DEBUG_OCC")) fprintf(stderr, "[ktf] pair kernel: %d co-resident clusters on %d SMs\n", n, ktf::num_sms());
   }
   const unsigned clusters = (unsigned)std::min<long long>(tiles, std::min(max_clusters[dev], ktf::num_sms() / 2));
-  tdnn_tc_pair_kernel<MODE><<<2 * clusters, kThreadsTc, kSmemPair, st>>>(tmA, tmB_half, tmC, args);
+  tdnn_tc_pair_kernel<MODE, EW><<<2 * clusters, kPairThreads, kSmemPair, st>>>(tmA, tmB_half, tmC, args);
   KTF_LAUNCH_OK();
   return KTF_OK;
 }
