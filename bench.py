@@ -610,7 +610,9 @@ def stage_plda(h, steps, warmup, n=50000):
         x = torch.randn((count, PLDA_DIM), generator=g, device=h.dev)
         return x / x.norm(dim=1, keepdim=True) * PLDA_DIM ** 0.5
     x_test, x_enroll = xvecs(hi - lo), xvecs(hi - lo)
-    scores = torch.empty((n, hi - lo), device=h.dev, dtype=torch.float32)        # this rank's block: 10 GB / G
+    # this rank's block (10 GB / G); the row pitch is padded to 16 bytes so that the boxed (TMA) stores apply at every G
+    ld = (hi - lo + 7) // 8 * 8
+    scores = torch.empty((n, ld), device=h.dev, dtype=torch.float32)[:, :hi - lo]
 
     counts = [parallel.shard_range(n, r, h.world)[1] - parallel.shard_range(n, r, h.world)[0] for r in range(h.world)]
 
@@ -664,7 +666,7 @@ def stage_plda(h, steps, warmup, n=50000):
             pairs.append((a, b))
     _, _, _, score_ms = h.timed(score_only, steps, 2)
     # compact output: the same scores rounded once to bfloat16, half the HBM write
-    scores16 = torch.empty((n, hi - lo), device=h.dev, dtype=torch.bfloat16)
+    scores16 = torch.empty((n, ld), device=h.dev, dtype=torch.bfloat16)[:, :hi - lo]
 
     def score_bf16(pairs):
         a, b = ev_pair(torch)
