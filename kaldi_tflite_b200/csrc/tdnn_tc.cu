@@ -64,6 +64,7 @@ enum { kModeBf16 = 0, kModeF32 = 1, kModeStats = 2 };
 
 // rowmap flags
 constexpr int kRowStore = 1, kRowFirst = 2, kRowLast = 4;
+constexpr int kRowFlagMask = 7;      // bits above hold splice bookkeeping (build_padded_kernel)
 
 struct TcArgs {
   int num_taps;
@@ -401,11 +402,12 @@ __device__ __forceinline__ void store_chunk2(const unsigned (&r)[32], const floa
           x[4 * h + 2] = fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 2]) + bb.z, relu_lo) + radd;
           x[4 * h + 3] = fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo) + radd;
         } else {
+          // (a launch with per-column scale / offset never carries a row addend: launch_gemm_pair_ew rejects the mix)
           const float4 ss = s4[2 * c8 + h], oo = o4[2 * c8 + h];
-          x[4 * h + 0] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 0]) + bb.x, relu_lo), ss.x, oo.x) + radd;
-          x[4 * h + 1] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 1]) + bb.y, relu_lo), ss.y, oo.y) + radd;
-          x[4 * h + 2] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 2]) + bb.z, relu_lo), ss.z, oo.z) + radd;
-          x[4 * h + 3] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo), ss.w, oo.w) + radd;
+          x[4 * h + 0] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 0]) + bb.x, relu_lo), ss.x, oo.x);
+          x[4 * h + 1] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 1]) + bb.y, relu_lo), ss.y, oo.y);
+          x[4 * h + 2] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 2]) + bb.z, relu_lo), ss.z, oo.z);
+          x[4 * h + 3] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo), ss.w, oo.w);
         }
       }
       if (OUT_BF16) {
@@ -790,7 +792,7 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int flags = 0;
         if (row < m_rows) flags = a.rowmap ? a.rowmap[row] : kRowStore;
         if (a.debug & 1) flags = 0;
-        const bool plain = __all_sync(0xffffffffu, flags == kRowStore);
+        const bool plain = __all_sync(0xffffffffu, (flags & kRowFlagMask) == kRowStore);
         float radd = 0.0f;
         if (a.row_add != nullptr && row < m_rows) radd = a.row_add[row];
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -1070,6 +1072,16 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       pre_nt = nt_;
     };
+    int nx_flags = 0;
+    float nx_radd = 0.0f;
+    auto load_row_meta = [&](long long row_, int& f_, float& ra_) {
+      f_ = 0;
+      ra_ = 0.0f;
+      if (row_ < m_rows) {
+        f_ = a.rowmap ? a.rowmap[row_] : kRowStore;
+        if (a.row_add != nullptr) ra_ = a.row_add[row_];
+      }
+    };
     int it = 0;
     for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
       long long mt;
@@ -1097,6 +1109,11 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
         wv_nt = nt;
       }
+      // this tile's row flags / row addend were requested one tile ahead (a global load in front of every tile was 9 % of
+      // the stall samples); request the next tile's now
+      int flags = nx_flags;
+      float radd = nx_radd;
+      if (it == 0) load_row_meta(row, flags, radd);
       {
         const long long next = tile + num_clusters;
         if (next < total_tiles) {
@@ -1104,16 +1121,14 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           int nt2;
           tile_coords<MODE>(next, m_tiles, n_tiles, a.reverse, a.group_m, mt2, nt2);
           if (nt2 != nt && pre_nt != nt2) prefetch_vec(nt2);
+          load_row_meta(mt2 * BM2 + (long long)rank * BM + quarter * 32 + lane, nx_flags, nx_radd);
         }
       }
-      int flags = 0;
-      if (row < m_rows) flags = a.rowmap ? a.rowmap[row] : kRowStore;
-      if (a.debug & 1) flags = 0;
-      const bool plain = __all_sync(0xffffffffu, flags == kRowStore);
-      float radd = 0.0f;
-      if (a.row_add != nullptr && row < m_rows) radd = a.row_add[row];
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (a.debug & 1) flags = 0;
+      // (the row map carries splice bookkeeping above bit 7: only the store / first / last bits decide the path)
+      const bool plain = __all_sync(0xffffffffu, (flags & kRowFlagMask) == kRowStore);
 
       const int n_cols = (int)n_rows;
       constexpr bool kBf16 = (MODE == kModeBf16);
@@ -1792,6 +1807,7 @@ int launch_gemm_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB_half, con
   constexpr int kSmemPair = PairCfg<EW>::kSmem;
   constexpr int kPairThreads = PairCfg<EW>::kThreads;
   TcArgs args = args_in;
+  if (args.row_add != nullptr && (args.scale != nullptr || args.offset != nullptr)) return KTF_EINVAL;
   CUtensorMap tmC = tmA;
   args.tma_store = 0;
   if (tma_store_enabled() && args.out != nullptr) {
