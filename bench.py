@@ -601,6 +601,7 @@ def stage_plda(h, steps, warmup, n=50000):
     import kaldi_tflite_b200 as ktf
     from kaldi_tflite_b200 import parallel
     torch = h.torch
+    n = int(os.environ.get("KTF_BENCH_PLDA_N", n))          # development knob (smaller all-vs-all problems)
     mean, Tm, psi = synthetic_plda(PLDA_DIM)
     layer = ktf.layers.PLDA(PLDA_DIM, mean, Tm, psi, dtype=np.float32, return_transformed=False)
     g = torch.Generator(device=h.dev).manual_seed(1234 + h.rank)

@@ -368,105 +368,110 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
   }
 }
 
-// Aligned (VEC) chunk store with TWO staging boxes per warp (pair kernel): the boxed store of pass p may still be
-// reading its box while pass p + 1 fills the other one -- the only wait is for the store issued two passes ago.
-// LEAN: the launch has no per-column scale / offset (PLDA scoring; TDNN layers whose BatchNorm was folded into the weights
-// and the next layer's bias): y = max(acc + bias, lo) (+ row addend) -- one vector instead of three, packed adds.
-template <bool OUT_BF16, bool LEAN, int VSTRIDE>
-__device__ __forceinline__ void store_chunk2(const unsigned (&r)[32], const float* vb, float relu_lo, float radd,
-                                             unsigned char* stg2, int& flip, int lane, int flags, bool plain,
-                                             unsigned char* out0, long long ld_bytes, const CUtensorMap* tmC, int tma_col,
-                                             int tma_row, bool& tma_pending, unsigned long long store_policy) {
+// Pair-kernel chunk store through 128-byte-wide staging boxes (32 rows x 128 bytes, the 128-byte TMA swizzle): a 32-column
+// chunk of fp32 rows fills a box, a chunk of bf16 rows fills half of one (HALF = chunk & 1) and the box leaves after the
+// second half -- one boxed store per 4 KB instead of one per 2 KB, i.e. half the fence / elect / issue sequences per tile.
+// NBOX = 2: the store of box p may still be reading while box p ^ 1 fills (the only wait is for the store issued two
+// boxes ago); NBOX = 1: the wait is for the previous store of the same box, issued a whole tile earlier for bf16 rows.
+// EPI: kEpiFull  y = scale * max(acc + bias, lo) + offset      (TDNN + ReLU + BatchNorm; never with a row addend)
+//      kEpiLean  y = max(acc + bias, lo) + row addend           (no per-column scale / offset)
+//      kEpiAdd   y = (acc + bias) + row addend                  (PLDA scoring: nothing to clamp)
+// all three round like the general form with scale 1 / offset 0 / lo = -FLT_MAX, so every path gives the same fp32 value.
+constexpr int kEpiFull = 0, kEpiLean = 1, kEpiAdd = 2;
+constexpr int kBoxRow = 128;                         // bytes per staged row of a box
+constexpr int kBoxBytes = 32 * kBoxRow;
+
+template <bool OUT_BF16, int EPI, int VSTRIDE, int NBOX, int HALF>
+__device__ __forceinline__ void store_box(const unsigned (&r)[32], const float* vb, float relu_lo, float radd,
+                                          unsigned char* stg2, int& flip, int lane, int flags, bool plain,
+                                          unsigned char* out_box, long long ld_bytes, const CUtensorMap* tmC, int tma_col,
+                                          int tma_row, bool& tma_pending, unsigned long long store_policy, int dbg) {
   const float4* b4 = reinterpret_cast<const float4*>(vb);
   const float4* s4 = reinterpret_cast<const float4*>(vb + VSTRIDE);
   const float4* o4 = reinterpret_cast<const float4*>(vb + 2 * VSTRIDE);
-  constexpr int kCols = kRowSeg / (OUT_BF16 ? 2 : 4);
-  constexpr int kPieces = kRowSeg / 16;
-  constexpr int kGroups = kCols / 8;
-  const int wsw = (lane >> 1) & 3;
+  constexpr int kVals = OUT_BF16 ? 4 : 8;              // 16-byte pieces this chunk contributes to a staged row
   const bool tma = plain && tmC != nullptr;
+  uint4 val[kVals];
 #pragma unroll
-  for (int pass = 0; pass < 32 / kCols; ++pass) {
-    uint4 val[OUT_BF16 ? kGroups : 2 * kGroups];
+  for (int c8 = 0; c8 < 4; ++c8) {
+    float x[8];
 #pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
-      const int c8 = pass * kGroups + g;
-      float x[8];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4 bb = b4[2 * c8 + h];
-        if (LEAN) {
-          // same association as the general form with scale 1 / offset 0, so every path rounds to the same fp32 value
-          x[4 * h + 0] = fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 0]) + bb.x, relu_lo) + radd;
-          x[4 * h + 1] = fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 1]) + bb.y, relu_lo) + radd;
-          x[4 * h + 2] = fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 2]) + bb.z, relu_lo) + radd;
-          x[4 * h + 3] = fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo) + radd;
-        } else {
-          // (a launch with per-column scale / offset never carries a row addend: launch_gemm_pair_ew rejects the mix)
-          const float4 ss = s4[2 * c8 + h], oo = o4[2 * c8 + h];
-          x[4 * h + 0] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 0]) + bb.x, relu_lo), ss.x, oo.x);
-          x[4 * h + 1] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 1]) + bb.y, relu_lo), ss.y, oo.y);
-          x[4 * h + 2] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 2]) + bb.z, relu_lo), ss.z, oo.z);
-          x[4 * h + 3] = fmaf(fmaxf(__uint_as_float(r[8 * c8 + 4 * h + 3]) + bb.w, relu_lo), ss.w, oo.w);
-        }
-      }
-      if (OUT_BF16) {
-        val[g] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                            pack_bf16x2(x[6], x[7]));
+    for (int h = 0; h < 2; ++h) {
+      const float4 bb = b4[2 * c8 + h];
+      const float a0 = __uint_as_float(r[8 * c8 + 4 * h + 0]), a1 = __uint_as_float(r[8 * c8 + 4 * h + 1]);
+      const float a2 = __uint_as_float(r[8 * c8 + 4 * h + 2]), a3 = __uint_as_float(r[8 * c8 + 4 * h + 3]);
+      if (EPI == kEpiAdd) {
+        x[4 * h + 0] = (a0 + bb.x) + radd;
+        x[4 * h + 1] = (a1 + bb.y) + radd;
+        x[4 * h + 2] = (a2 + bb.z) + radd;
+        x[4 * h + 3] = (a3 + bb.w) + radd;
+      } else if (EPI == kEpiLean) {
+        x[4 * h + 0] = fmaxf(a0 + bb.x, relu_lo) + radd;
+        x[4 * h + 1] = fmaxf(a1 + bb.y, relu_lo) + radd;
+        x[4 * h + 2] = fmaxf(a2 + bb.z, relu_lo) + radd;
+        x[4 * h + 3] = fmaxf(a3 + bb.w, relu_lo) + radd;
       } else {
-        val[2 * g] = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
-        val[2 * g + 1] = make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7]));
+        const float4 ss = s4[2 * c8 + h], oo = o4[2 * c8 + h];
+        x[4 * h + 0] = fmaf(fmaxf(a0 + bb.x, relu_lo), ss.x, oo.x);
+        x[4 * h + 1] = fmaf(fmaxf(a1 + bb.y, relu_lo), ss.y, oo.y);
+        x[4 * h + 2] = fmaf(fmaxf(a2 + bb.z, relu_lo), ss.z, oo.z);
+        x[4 * h + 3] = fmaf(fmaxf(a3 + bb.w, relu_lo), ss.w, oo.w);
       }
     }
-    unsigned char* stg = stg2 + flip * (32 * kRowSeg);
-    if (tma_pending) {                             // at most one boxed store (the other box) stays in flight
+    if (OUT_BF16) {
+      val[c8] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                           pack_bf16x2(x[6], x[7]));
+    } else {
+      val[2 * c8] = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+      val[2 * c8 + 1] = make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7]));
+    }
+  }
+  unsigned char* stg = stg2 + (NBOX == 2 ? flip * kBoxBytes : 0);
+  constexpr bool kOpens = !OUT_BF16 || HALF == 0;      // this chunk writes the first bytes of the box
+  constexpr bool kCloses = !OUT_BF16 || HALF == 1;     // ... the last ones: the box leaves
+  if (kOpens && tma_pending) {
+    if (tma && NBOX == 2) {                            // at most one boxed store (the other box) stays in flight
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
-      __syncwarp();
-    }
-    uint4* mine = reinterpret_cast<uint4*>(stg + lane * kRowSeg);
-#pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
-      if (OUT_BF16) {
-        mine[g ^ wsw] = val[g];
-      } else {
-        mine[(2 * g) ^ wsw] = val[2 * g];
-        mine[(2 * g + 1) ^ wsw] = val[2 * g + 1];
-      }
-    }
-    flip ^= 1;
-    if (tma) {
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (store_policy != 0ull) tma_store_2d_hint(tmC, stg, tma_col + pass * kCols, tma_row, store_policy);
-        else tma_store_2d(tmC, stg, tma_col + pass * kCols, tma_row);
-      }
-      tma_pending = true;
-      continue;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < kPieces; ++j) {
-      const int q = j * 32 + lane, rr = q / kPieces, part = q % kPieces;
-      const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kRowSeg + ((part ^ ((rr >> 1) & 3)) * 16));
-      unsigned char* dst = out0 + rr * ld_bytes + pass * kRowSeg + part * 16;
-      if (plain) {
-        *reinterpret_cast<uint4*>(dst) = v;
-        continue;
-      }
-      const int f = __shfl_sync(0xffffffffu, flags, rr);
-      if (f & kRowStore) {
-        *reinterpret_cast<uint4*>(dst) = v;
-        if (f & (kRowFirst | kRowLast)) {
-          const int lo = (f & kRowFirst) ? kHalo : 0, hi = (f & kRowLast) ? kHalo : 0;
-#pragma unroll 1
-          for (int h = -lo; h <= hi; ++h)
-            if (h != 0) *reinterpret_cast<uint4*>(dst + h * ld_bytes) = v;
-        }
-      }
+    } else {                                           // (the per-row path commits no group: drain before reusing a box)
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      tma_pending = false;
     }
     __syncwarp();
   }
+  uint4* mine = reinterpret_cast<uint4*>(stg + lane * kBoxRow);
+  const int wsw = lane & 7;
+#pragma unroll
+  for (int g = 0; g < kVals; ++g) mine[((OUT_BF16 ? HALF * 4 : 0) + g) ^ wsw] = val[g];
+  if (!kCloses) return;
+  if (NBOX == 2) flip ^= 1;
+  if (tma) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && !(dbg & 4)) {                     // (ablation bit 4: boxes are filled but never leave)
+      if (store_policy != 0ull) tma_store_2d_hint(tmC, stg, tma_col, tma_row, store_policy);
+      else tma_store_2d(tmC, stg, tma_col, tma_row);
+    }
+    tma_pending = true;
+    return;
+  }
+  __syncwarp();
+#pragma unroll 2
+  for (int j = 0; j < 8; ++j) {                        // 32 rows x 8 pieces, a lane moves one 16-byte piece per step
+    const int q = j * 32 + lane, rr = q >> 3, part = q & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kBoxRow + ((part ^ (rr & 7)) * 16));
+    unsigned char* dst = out_box + rr * ld_bytes + part * 16;
+    const int f = __shfl_sync(0xffffffffu, flags, rr);
+    if (f & kRowStore) {
+      *reinterpret_cast<uint4*>(dst) = v;
+      if (f & (kRowFirst | kRowLast)) {
+        const int lo = (f & kRowFirst) ? kHalo : 0, hi = (f & kRowLast) ? kHalo : 0;
+#pragma unroll 1
+        for (int h = -lo; h <= hi; ++h)
+          if (h != 0) *reinterpret_cast<uint4*>(dst + h * ld_bytes) = v;
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // Ragged / unaligned chunk of the pair kernel (right edge of the matrix, output pitch not a multiple of 16 bytes): fp32
@@ -858,15 +863,16 @@ constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
 // TMEM load -> per-column vectors -> staging -> boxed store); 16 warps double the chains in flight.  They pay for it
 // with one ring stage (4 x 32 KB instead of 5) and 112 registers per thread.
 template <int EW> struct PairCfg {
-  static constexpr int kStages = EW == 16 ? 4 : 5;
+  static constexpr int kStages = 4;
   static constexpr int kThreads = 64 + EW * 32;
   static constexpr int kCols = BN / (EW / 4);              // tile columns per epilogue warp: 128 or 64
   static constexpr int kChunks = kCols / 32;
-  static constexpr int kStgBytes = EW * 2 * 32 * kRowSeg;  // two 32-row x 64-byte boxes per epilogue warp
+  static constexpr int kBoxes = EW == 16 ? 1 : 2;          // 32-row x 128-byte staging boxes per epilogue warp
+  static constexpr int kStgBytes = EW * kBoxes * kBoxBytes;
   static constexpr int kVecBytes = EW * 3 * kCols * 4;     // per-warp [bias | scale | offset] of the warp's columns
   static constexpr int kSmem = kStages * kPairStageBytes + 1024 + 256 + kVecBytes + kStgBytes;
 };
-static_assert(PairCfg<8>::kSmem <= 227 * 1024 && PairCfg<16>::kSmem <= 227 * 1024, "pair kernel shared memory");
+static_assert(PairCfg<8>::kSmem <= 226 * 1024 && PairCfg<16>::kSmem <= 226 * 1024, "pair kernel shared memory");
 
 __device__ __forceinline__ unsigned cluster_ctarank() {
   unsigned r;
@@ -927,7 +933,7 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + kPairStages * kPairABytes;
-  unsigned char* s_stg = smem + kPairStages * kPairStageBytes;          // [EW][2][32][kRowSeg] boxes (512 B aligned)
+  unsigned char* s_stg = smem + kPairStages * kPairStageBytes;          // [EW][kBoxes] boxes of 32 rows x 128 bytes (1024-byte aligned)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_stg + Cfg::kStgBytes);
   unsigned long long* full_bar = bars;                        // [kPairStages]   (used in the leader)
   unsigned long long* empty_bar = bars + kPairStages;         // [kPairStages]
@@ -947,6 +953,10 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n_tiles = (int)((n_rows + BN - 1) / BN);
   const long long total_tiles = m_tiles * n_tiles;
   const int num_kb = a.num_taps * a.kblocks_per_tap;
+  const long long t_begin = cluster_id, t_end = total_tiles, t_step = num_clusters;   // this cluster's tiles
+  auto coords = [&](long long tile_, long long& mt_, int& nt_) {
+    tile_coords<MODE>(tile_, m_tiles, n_tiles, a.reverse, a.group_m, mt_, nt_);
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kPairStages; ++s) {
@@ -978,15 +988,15 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (a.tma_store) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmC) : "memory");
       int stage = 0;
       unsigned phase = 0;
-      for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      for (long long tile = t_begin; tile < t_end; tile += t_step) {
         long long mt;
         int nt;
-        tile_coords<MODE>(tile, m_tiles, n_tiles, a.reverse, a.group_m, mt, nt);
+        coords(tile, mt, nt);
         const int m0 = (int)(mt * BM2) + (int)rank * BM, n0 = nt * BN + (int)rank * (BN / 2);
-        if (a.act_base != nullptr && rank == 0 && tile + num_clusters < total_tiles) {
+        if (a.act_base != nullptr && rank == 0 && tile + t_step < t_end) {
           long long mt2;
           int nt2;
-          tile_coords<MODE>(tile + num_clusters, m_tiles, n_tiles, a.reverse, a.group_m, mt2, nt2);
+          coords(tile + t_step, mt2, nt2);
           if (nt2 == 0) {                                    // one cluster per row block requests it for all its n-tiles
             long long r0 = mt2 * BM2 - kHalo, r1 = r0 + BM2 + 2 * kHalo;
             r0 = r0 < 0 ? 0 : r0;
@@ -1002,7 +1012,8 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int wcol = tap * a.tap_cols + d0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const unsigned full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);   // both CTAs' bytes land on this barrier
+          // both CTAs' bytes land on the leader's barrier
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
           else mbar_arrive_cluster(full_leader);
           tma_load_2d_pair(sA + stage * kPairABytes, &tmA, full_leader, d0, m0 + a.ctx[tap]);
           tma_load_2d_pair(sB + stage * kPairBBytes, &tmB, full_leader, wcol, n0);
@@ -1019,7 +1030,7 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       unsigned phase = 0;
       int it = 0;
-      for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+      for (long long tile = t_begin; tile < t_end; tile += t_step, ++it) {
         const int acc = it & 1;
         const unsigned acc_phase = (unsigned)(it >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -1083,10 +1094,10 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     };
     int it = 0;
-    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+    for (long long tile = t_begin; tile < t_end; tile += t_step, ++it) {
       long long mt;
       int nt;
-      tile_coords<MODE>(tile, m_tiles, n_tiles, a.reverse, a.group_m, mt, nt);
+      coords(tile, mt, nt);
       const int col_base = nt * BN;
       const int acc = it & 1;
       const unsigned acc_phase = (unsigned)(it >> 1) & 1u;
@@ -1115,11 +1126,11 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float radd = nx_radd;
       if (it == 0) load_row_meta(row, flags, radd);
       {
-        const long long next = tile + num_clusters;
-        if (next < total_tiles) {
+        const long long next = tile + t_step;
+        if (next < t_end) {
           long long mt2;
           int nt2;
-          tile_coords<MODE>(next, m_tiles, n_tiles, a.reverse, a.group_m, mt2, nt2);
+          coords(next, mt2, nt2);
           if (nt2 != nt && pre_nt != nt2) prefetch_vec(nt2);
           load_row_meta(mt2 * BM2 + (long long)rank * BM + quarter * 32 + lane, nx_flags, nx_radd);
         }
@@ -1135,40 +1146,53 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr int kEs = kBf16 ? 2 : 4;
       const long long ld_bytes = a.out_ld * kEs;
       unsigned char* owarp = reinterpret_cast<unsigned char*>(a.out) + (row0 + quarter * 32) * ld_bytes;
-      unsigned char* stg2 = s_stg + (warp - 2) * (2 * 32 * kRowSeg);
+      unsigned char* stg2 = s_stg + (warp - 2) * (Cfg::kBoxes * kBoxBytes);
       const bool vec_ok = ((reinterpret_cast<unsigned long long>(a.out) | (unsigned long long)ld_bytes) & 15ull) == 0;
       const float relu_lo = a.relu ? 0.0f : -3.402823466e+38f;
+      const int epi = lean ? (a.relu ? kEpiLean : kEpiAdd) : kEpiFull;   // launch-uniform
       // EW = 8: TMEM loads run one chunk ahead of the math (two register buffers); EW = 16 has the warps to cover the
       // load latency and 96 registers per thread: one buffer
       constexpr int kRB = EW == 16 ? 1 : 2;
+      constexpr int kNB = Cfg::kBoxes;
       unsigned r[kRB][32];
       tmem_ld32_issue(taddr0, r[0]);
 #pragma unroll
       for (int c = 0; c < kPChunks; ++c) {
         tmem_ld_wait(r[c % kRB]);
         if (kRB == 2 && c + 1 < kPChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) % kRB]);
-        const int cc = colq * kPCols + c * 32;
-        const int col0 = col_base + cc;
+        const int col0 = col_base + colq * kPCols + c * 32;
+        // the 128-byte box this chunk belongs to: the chunk itself (fp32 rows) or a pair of chunks (bf16 rows)
+        const int box_col0 = kBf16 ? col_base + colq * kPCols + (c & ~1) * 32 : col0;
+        constexpr int kBoxCols = kBoxRow / kEs;
         if (col0 >= n_cols || (a.debug & 2)) {
           if (kRB == 1 && c + 1 < kPChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[0]);
           continue;
         }
-        unsigned char* out0 = owarp + (long long)col0 * kEs;
         const int trow = (int)row0 + quarter * 32;
-        if (vec_ok && col0 + 32 <= n_cols) {
-          if (lean)
-            store_chunk2<kBf16, true, kPCols>(r[c % kRB], wv + c * 32, relu_lo, radd, stg2, stg_flip, lane, flags, plain,
-                                                out0, ld_bytes, tmc, col0, trow, tma_pending, store_policy);
-          else
-            store_chunk2<kBf16, false, kPCols>(r[c % kRB], wv + c * 32, relu_lo, radd, stg2, stg_flip, lane, flags, plain,
-                                                 out0, ld_bytes, tmc, col0, trow, tma_pending, store_policy);
+        if (vec_ok && box_col0 + kBoxCols <= n_cols) {
+          unsigned char* out_box = owarp + (long long)box_col0 * kEs;
+          const float* wvc = wv + c * 32;
+#define KTF_STORE_BOX(EPI_, HALF_)                                                                                      \
+  store_box<kBf16, EPI_, kPCols, kNB, HALF_>(r[c % kRB], wvc, relu_lo, radd, stg2, stg_flip, lane, flags, plain, out_box, \
+                                             ld_bytes, tmc, box_col0, trow, tma_pending, store_policy, a.debug)
+          if ((c & 1) == 0) {
+            if (epi == kEpiFull) KTF_STORE_BOX(kEpiFull, 0);
+            else if (epi == kEpiAdd) KTF_STORE_BOX(kEpiAdd, 0);
+            else KTF_STORE_BOX(kEpiLean, 0);
+          } else {
+            if (epi == kEpiFull) KTF_STORE_BOX(kEpiFull, 1);
+            else if (epi == kEpiAdd) KTF_STORE_BOX(kEpiAdd, 1);
+            else KTF_STORE_BOX(kEpiLean, 1);
+          }
+#undef KTF_STORE_BOX
         } else {
           if (tma_pending) {                     // the ragged path reads back with the generic proxy: no box in flight
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
             __syncwarp();
             tma_pending = false;
           }
-          // (the warp's two boxes, 4 KB, serve as the fp32 staging of the ragged path)
+          // (the warp's staging boxes serve as the fp32 staging of the ragged path)
+          unsigned char* out0 = owarp + (long long)col0 * kEs;
           store_chunk_ragged<kBf16, kPCols>(r[c % kRB], wv + c * 32, lean, relu_lo, radd, stg2, lane, flags, out0, ld_bytes,
                                             n_cols - col0);
         }
@@ -1674,20 +1698,22 @@ int encode_map(CUtensorMap* map, const void* base, unsigned long long inner, uns
 }
 
 // Output map for the TMA-store epilogue: row-major (rows, cols) matrix of 2-byte (bf16) or 4-byte (fp32) elements, boxes
-// of 32 rows x 64 bytes with the 64-byte swizzle (the layout store_chunk stages).  Returns false when the matrix cannot
+// of 32 rows x 64 bytes with the 64-byte swizzle (the layout store_chunk stages) or 32 rows x 128 bytes with the 128-byte
+// swizzle (store_box, pair kernel).  Returns false when the matrix cannot
 // be described (unaligned base / pitch): the epilogue then keeps its st.global path.
 bool encode_map_out(CUtensorMap* map, const void* base, int elem_bytes, unsigned long long cols, unsigned long long rows,
-                    unsigned long long ld_elems) {
+                    unsigned long long ld_elems, int row_bytes = kRowSeg) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr || base == nullptr || rows == 0 || cols == 0) return false;
   if ((reinterpret_cast<unsigned long long>(base) & 15ull) != 0 || ((ld_elems * elem_bytes) & 15ull) != 0) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld_elems * elem_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)(kRowSeg / elem_bytes), 32};
+  cuuint32_t box[2] = {(cuuint32_t)(row_bytes / elem_bytes), 32};
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -1799,7 +1825,7 @@ int launch_gemm_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB_half, con
 template <int MODE>
 int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const TcArgs& args_in, cudaStream_t st) {
   return pair_epi_warps(MODE == kModeBf16) == 16 ? launch_gemm_pair_ew<MODE, 16>(tmA, tmB_half, args_in, st)
-                                : launch_gemm_pair_ew<MODE, 8>(tmA, tmB_half, args_in, st);
+                                                 : launch_gemm_pair_ew<MODE, 8>(tmA, tmB_half, args_in, st);
 }
 
 template <int MODE, int EW>
@@ -1813,7 +1839,7 @@ int launch_gemm_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB_half, con
   if (tma_store_enabled() && args.out != nullptr) {
     const int es = (MODE == kModeBf16) ? 2 : 4;
     if (encode_map_out(&tmC, args.out, es, (unsigned long long)args.n_rows, (unsigned long long)args.m_rows,
-                       (unsigned long long)args.out_ld))
+                       (unsigned long long)args.out_ld, kBoxRow))
       args.tma_store = 1;
   }
   static unsigned long long attr_done = 0;
