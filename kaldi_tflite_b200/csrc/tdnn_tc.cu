@@ -98,7 +98,9 @@ struct TcArgs {
                             // evict-last L2 policy and the boxed stores evict-first, so the stream does not push the
                             // operands out to HBM (measured without: 3.4-4.3 GB of DRAM reads for 76 MB of inputs)
   int reverse;              // walk the tiles from the last row block to the first (see launch_gemm)
-  int debug;                // development knobs (KTF_TC_DEBUG): 1 = skip global stores, 2 = skip the epilogue math
+  int debug;                // development knobs (KTF_TC_DEBUG): 1 = skip global stores, 2 = skip the epilogue math,
+                            // 4 = stage the boxes but never issue their stores
+  long long* trace;         // development (KTF_TC_TRACE=file): clock64 of cluster 0's tile phases, 4 slots per tile
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -858,16 +860,16 @@ tdnn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 constexpr int kPairABytes = BM * BK * 2;                 // 16 KB: this CTA's 128 rows
 constexpr int kPairBBytes = (BN / 2) * BK * 2;           // 16 KB: this CTA's 128 of the tile's 256 columns
 constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
-// EW epilogue warps per CTA (8 or 16: EW / 4 warps share a TMEM lane quarter and split the tile's 256 columns).  The
-// epilogue of the short-K layers and of PLDA scoring is latency-bound (a thread owns one accumulator row and walks
-// TMEM load -> per-column vectors -> staging -> boxed store); 16 warps double the chains in flight.  They pay for it
-// with one ring stage (4 x 32 KB instead of 5) and 112 registers per thread.
+// EW epilogue warps per CTA (8 or 16: EW / 4 warps share a TMEM lane quarter and split the tile's 256 columns).  A thread
+// owns one accumulator row and walks TMEM load -> per-column vectors -> staging box -> boxed store; 16 warps double the
+// chains in flight and pay for it with one ring stage (4 x 32 KB instead of 5) and 96 registers per thread.  Which one a
+// launch gets: pair_epi_warps().
 template <int EW> struct PairCfg {
-  static constexpr int kStages = 4;
+  static constexpr int kStages = EW == 16 ? 4 : 5;
   static constexpr int kThreads = 64 + EW * 32;
   static constexpr int kCols = BN / (EW / 4);              // tile columns per epilogue warp: 128 or 64
   static constexpr int kChunks = kCols / 32;
-  static constexpr int kBoxes = EW == 16 ? 1 : 2;          // 32-row x 128-byte staging boxes per epilogue warp
+  static constexpr int kBoxes = 1;                         // 32-row x 128-byte staging boxes per epilogue warp
   static constexpr int kStgBytes = EW * kBoxes * kBoxBytes;
   static constexpr int kVecBytes = EW * 3 * kCols * 4;     // per-warp [bias | scale | offset] of the warp's columns
   static constexpr int kSmem = kStages * kPairStageBytes + 1024 + 256 + kVecBytes + kStgBytes;
@@ -1035,10 +1037,13 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const unsigned acc_phase = (unsigned)(it >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (a.trace != nullptr && cluster_id == 0 && it < 512) a.trace[4 * it + 0] = clock64();   // accumulator free
         const unsigned tmem_d = tmem_base + (unsigned)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == num_kb - 1 && a.trace != nullptr && cluster_id == 0 && it < 512)
+            a.trace[4 * it + 1] = clock64();                                                       // last operands landed
           const unsigned long long adesc = umma_desc(smem_u32(sA + stage * kPairABytes));
           const unsigned long long bdesc = umma_desc(smem_u32(sB + stage * kPairBBytes));
 #pragma unroll
@@ -1137,6 +1142,8 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (a.trace != nullptr && cluster_id == 0 && rank == 0 && warp == 2 && lane == 0 && it < 512)
+        a.trace[4 * it + 2] = clock64();                                                           // accumulator full
       if (a.debug & 1) flags = 0;
       // (the row map carries splice bookkeeping above bit 7: only the store / first / last bits decide the path)
       const bool plain = __all_sync(0xffffffffu, (flags & kRowFlagMask) == kRowStore);
@@ -1203,6 +1210,8 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) {
         if (rank == 0) mbar_arrive(&tempty_bar[acc]);
         else mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        if (a.trace != nullptr && cluster_id == 0 && rank == 0 && warp == 2 && it < 512)
+          a.trace[4 * it + 3] = clock64();                                                         // warp 2 drained its part
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // smem outlives the last boxes
@@ -1806,17 +1815,19 @@ int pair_enabled() {
 
 // CTA-pair launch of a row-storing mode.  tmB must be encoded with 128-row boxes (each CTA loads half of the tile's 256
 // columns); everything else as launch_gemm.
-// Epilogue warps per CTA of the pair kernel.  Measured (config 3 / wav2xvec / PLDA 50 000^2): 16 warps win for bf16 rows
-// (0.798 vs 0.834 ms, 4.62 vs 4.79 ms), 8 warps for fp32 rows (2.61 vs 2.73 ms: two staging passes per chunk and 96
-// registers do not mix).  KTF_TC_PAIR_EPI_WARPS overrides both.
-int pair_epi_warps(bool bf16_rows) {
+// Epilogue warps per CTA of the pair kernel.  The per-tile trace (KTF_TC_TRACE) shows which side waits: with K <= 256
+// (tdnn1) the accumulator is ready long before the 16 epilogue warps are done -- epilogue-bound, 16 warps win (period 5.1 k
+// against 5.5 k clocks with 8); from K = 384 up the MMA thread waits for operands (tdnn4: 6.9 k of 7.5 k clocks per tile),
+// the epilogue has slack, and what helps is the fifth ring stage that 8 warps leave room for (tdnn4 7.5 k -> 6.4 k clocks,
+// tdnn2 / tdnn3 16.1 k -> 14.7 k, PLDA 2.55 -> 2.42 ms).  KTF_TC_PAIR_EPI_WARPS overrides the choice.
+int pair_epi_warps(int num_kb) {
   static int ew = -1;
   if (ew < 0) {
     const char* e = getenv("KTF_TC_PAIR_EPI_WARPS");
     ew = e ? atoi(e) : 0;
   }
   if (ew == 8 || ew == 16) return ew;
-  return bf16_rows ? 16 : 8;
+  return num_kb <= 4 ? 16 : 8;
 }
 
 template <int MODE, int EW>
@@ -1824,8 +1835,9 @@ int launch_gemm_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB_half, con
 
 template <int MODE>
 int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB_half, const TcArgs& args_in, cudaStream_t st) {
-  return pair_epi_warps(MODE == kModeBf16) == 16 ? launch_gemm_pair_ew<MODE, 16>(tmA, tmB_half, args_in, st)
-                                                 : launch_gemm_pair_ew<MODE, 8>(tmA, tmB_half, args_in, st);
+  return pair_epi_warps(args_in.num_taps * args_in.kblocks_per_tap) == 16
+             ? launch_gemm_pair_ew<MODE, 16>(tmA, tmB_half, args_in, st)
+             : launch_gemm_pair_ew<MODE, 8>(tmA, tmB_half, args_in, st);
 }
 
 template <int MODE, int EW>
@@ -1880,8 +1892,29 @@ int launch_gemm_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB_half, con
     if (getenv("KTF_TC_DEBUG_OCC")) fprintf(stderr, "[ktf] pair kernel: %d co-resident clusters on %d SMs\n", n, ktf::num_sms());
   }
   const unsigned clusters = (unsigned)std::min<long long>(tiles, std::min(max_clusters[dev], ktf::num_sms() / 2));
+  // development: KTF_TC_TRACE=file appends, per launch, the clock64 stamps of cluster 0's first 512 tiles
+  // (accumulator free / last operands landed / accumulator full / epilogue warp done) -- synchronises, never on by default
+  static const char* trace_path = getenv("KTF_TC_TRACE");
+  static long long* trace_dev = nullptr;
+  if (trace_path != nullptr) {
+    if (trace_dev == nullptr) KTF_CUDA(cudaMalloc(&trace_dev, 2048 * sizeof(long long)));
+    KTF_CUDA(cudaMemsetAsync(trace_dev, 0, 2048 * sizeof(long long), st));
+    args.trace = trace_dev;
+  }
   tdnn_tc_pair_kernel<MODE, EW><<<2 * clusters, kPairThreads, kSmemPair, st>>>(tmA, tmB_half, tmC, args);
   KTF_LAUNCH_OK();
+  if (trace_path != nullptr) {
+    std::vector<long long> h(2048);
+    KTF_CUDA(cudaStreamSynchronize(st));
+    KTF_CUDA(cudaMemcpy(h.data(), trace_dev, 2048 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "a")) {
+      fprintf(f, "launch mode=%d ew=%d m=%lld n=%lld kb=%d clusters=%u\n", MODE, EW, args.m_rows, args.n_rows,
+              args.num_taps * args.kblocks_per_tap, clusters);
+      for (int i = 0; i < 512 && h[4 * i] != 0; ++i)
+        fprintf(f, "%d %lld %lld %lld %lld\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      fclose(f);
+    }
+  }
   return KTF_OK;
 }
 
@@ -2094,7 +2127,7 @@ int tc_gemm_nt(const void* A, long long m, long long lda, const void* B, long lo
   // streaming output (PLDA: the score matrix), operands re-read by every tile: see TcArgs::l2_stream_out
   args.l2_stream_out = ((double)m * (double)n * (c_bf16 ? 2.0 : 4.0) > 64e6) ? 1 : 0;
   if (const char* e = getenv("KTF_TC_L2_HINTS")) args.l2_stream_out = atoi(e);
-  args.group_m = (n + BN - 1) / BN > 8 ? 16 : 0;
+  args.group_m = (n + BN - 1) / BN > 8 ? 32 : 0;     // (measured at 50 000^2: 1 -> 2.77, 8 -> 2.61, 16 -> 2.54, 32 -> 2.47-2.51, 64 -> 2.65 ms)
   if (const char* e = getenv("KTF_TC_GROUP_M")) args.group_m = atoi(e);
   if (pair_enabled()) {
     CUtensorMap tmBh;
