@@ -781,7 +781,7 @@ def roofline_for(workload, r, pk):
                 "frac": achieved / pk["tf_sustained"], "peak_burst": pk["tf_burst"],
                 "frac_of_burst": achieved / pk["tf_burst"], "traffic": traffic, "traffic_source": src,
                 "peak_source": pk["src"] + " bf16_tflops_sustained (kernels timed inside a long step); burst beside it",
-                "kernel": "tdnn_tc_kernel x7 (tcgen05 implicit-GEMM stack incl. splice / finalize launches)",
+                "kernel": "tdnn_tc_pair_kernel x5 + tdnn_tc_kernel<STATS> (tcgen05 implicit-GEMM stack incl. pre-pass / finalize launches)",
                 "kernel_ms": ms, "algorithmic_flops_per_launch": flops}
     achieved = r["score_bytes"] / (r["score_ms"] * 1e-3) / 1e9
     traffic, src = measured_traffic("plda_score")

@@ -373,8 +373,8 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
 // Pair-kernel chunk store through 128-byte-wide staging boxes (32 rows x 128 bytes, the 128-byte TMA swizzle): a 32-column
 // chunk of fp32 rows fills a box, a chunk of bf16 rows fills half of one (HALF = chunk & 1) and the box leaves after the
 // second half -- one boxed store per 4 KB instead of one per 2 KB, i.e. half the fence / elect / issue sequences per tile.
-// NBOX = 2: the store of box p may still be reading while box p ^ 1 fills (the only wait is for the store issued two
-// boxes ago); NBOX = 1: the wait is for the previous store of the same box, issued a whole tile earlier for bf16 rows.
+// A warp has ONE box: before refilling it waits for its previous store to have read the box (issued a whole tile
+// earlier for bf16 rows with 16 warps; two boxes per warp measured equal and cost a ring stage).
 // EPI: kEpiFull  y = scale * max(acc + bias, lo) + offset      (TDNN + ReLU + BatchNorm; never with a row addend)
 //      kEpiLean  y = max(acc + bias, lo) + row addend           (no per-column scale / offset)
 //      kEpiAdd   y = (acc + bias) + row addend                  (PLDA scoring: nothing to clamp)
@@ -383,9 +383,9 @@ constexpr int kEpiFull = 0, kEpiLean = 1, kEpiAdd = 2;
 constexpr int kBoxRow = 128;                         // bytes per staged row of a box
 constexpr int kBoxBytes = 32 * kBoxRow;
 
-template <bool OUT_BF16, int EPI, int VSTRIDE, int NBOX, int HALF>
+template <bool OUT_BF16, int EPI, int VSTRIDE, int HALF>
 __device__ __forceinline__ void store_box(const unsigned (&r)[32], const float* vb, float relu_lo, float radd,
-                                          unsigned char* stg2, int& flip, int lane, int flags, bool plain,
+                                          unsigned char* stg, int lane, int flags, bool plain,
                                           unsigned char* out_box, long long ld_bytes, const CUtensorMap* tmC, int tma_col,
                                           int tma_row, bool& tma_pending, unsigned long long store_policy, int dbg) {
   const float4* b4 = reinterpret_cast<const float4*>(vb);
@@ -428,16 +428,11 @@ __device__ __forceinline__ void store_box(const unsigned (&r)[32], const float* 
       val[2 * c8 + 1] = make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7]));
     }
   }
-  unsigned char* stg = stg2 + (NBOX == 2 ? flip * kBoxBytes : 0);
   constexpr bool kOpens = !OUT_BF16 || HALF == 0;      // this chunk writes the first bytes of the box
   constexpr bool kCloses = !OUT_BF16 || HALF == 1;     // ... the last ones: the box leaves
-  if (kOpens && tma_pending) {
-    if (tma && NBOX == 2) {                            // at most one boxed store (the other box) stays in flight
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
-    } else {                                           // (the per-row path commits no group: drain before reusing a box)
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-      tma_pending = false;
-    }
+  if (kOpens && tma_pending) {                         // the box's previous store has finished reading it
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    tma_pending = false;
     __syncwarp();
   }
   uint4* mine = reinterpret_cast<uint4*>(stg + lane * kBoxRow);
@@ -445,7 +440,6 @@ __device__ __forceinline__ void store_box(const unsigned (&r)[32], const float* 
 #pragma unroll
   for (int g = 0; g < kVals; ++g) mine[((OUT_BF16 ? HALF * 4 : 0) + g) ^ wsw] = val[g];
   if (!kCloses) return;
-  if (NBOX == 2) flip ^= 1;
   if (tma) {
     fence_proxy_async_smem();
     __syncwarp();
@@ -869,8 +863,7 @@ template <int EW> struct PairCfg {
   static constexpr int kThreads = 64 + EW * 32;
   static constexpr int kCols = BN / (EW / 4);              // tile columns per epilogue warp: 128 or 64
   static constexpr int kChunks = kCols / 32;
-  static constexpr int kBoxes = 1;                         // 32-row x 128-byte staging boxes per epilogue warp
-  static constexpr int kStgBytes = EW * kBoxes * kBoxBytes;
+  static constexpr int kStgBytes = EW * kBoxBytes;         // one 32-row x 128-byte staging box per epilogue warp
   static constexpr int kVecBytes = EW * 3 * kCols * 4;     // per-warp [bias | scale | offset] of the warp's columns
   static constexpr int kSmem = kStages * kPairStageBytes + 1024 + 256 + kVecBytes + kStgBytes;
 };
@@ -935,7 +928,7 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + kPairStages * kPairABytes;
-  unsigned char* s_stg = smem + kPairStages * kPairStageBytes;          // [EW][kBoxes] boxes of 32 rows x 128 bytes (1024-byte aligned)
+  unsigned char* s_stg = smem + kPairStages * kPairStageBytes;          // [EW] boxes of 32 rows x 128 bytes (1024-byte aligned)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_stg + Cfg::kStgBytes);
   unsigned long long* full_bar = bars;                        // [kPairStages]   (used in the leader)
   unsigned long long* empty_bar = bars + kPairStages;         // [kPairStages]
@@ -1061,7 +1054,6 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;
     const int colq = (warp - 2) >> 2;
     bool tma_pending = false;
-    int stg_flip = 0;                          // which of the warp's two staging boxes the next pass writes
     const bool lean = a.scale == nullptr && a.offset == nullptr;   // launch-uniform: bias (+ ReLU, + row addend) only
     const unsigned long long store_policy = a.l2_stream_out ? l2_policy_evict_first() : 0ull;
     const CUtensorMap* tmc = a.tma_store ? &tmC : nullptr;
@@ -1153,14 +1145,13 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr int kEs = kBf16 ? 2 : 4;
       const long long ld_bytes = a.out_ld * kEs;
       unsigned char* owarp = reinterpret_cast<unsigned char*>(a.out) + (row0 + quarter * 32) * ld_bytes;
-      unsigned char* stg2 = s_stg + (warp - 2) * (Cfg::kBoxes * kBoxBytes);
+      unsigned char* stg2 = s_stg + (warp - 2) * kBoxBytes;
       const bool vec_ok = ((reinterpret_cast<unsigned long long>(a.out) | (unsigned long long)ld_bytes) & 15ull) == 0;
       const float relu_lo = a.relu ? 0.0f : -3.402823466e+38f;
       const int epi = lean ? (a.relu ? kEpiLean : kEpiAdd) : kEpiFull;   // launch-uniform
       // EW = 8: TMEM loads run one chunk ahead of the math (two register buffers); EW = 16 has the warps to cover the
       // load latency and 96 registers per thread: one buffer
       constexpr int kRB = EW == 16 ? 1 : 2;
-      constexpr int kNB = Cfg::kBoxes;
       unsigned r[kRB][32];
       tmem_ld32_issue(taddr0, r[0]);
 #pragma unroll
@@ -1180,8 +1171,8 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           unsigned char* out_box = owarp + (long long)box_col0 * kEs;
           const float* wvc = wv + c * 32;
 #define KTF_STORE_BOX(EPI_, HALF_)                                                                                      \
-  store_box<kBf16, EPI_, kPCols, kNB, HALF_>(r[c % kRB], wvc, relu_lo, radd, stg2, stg_flip, lane, flags, plain, out_box, \
-                                             ld_bytes, tmc, box_col0, trow, tma_pending, store_policy, a.debug)
+  store_box<kBf16, EPI_, kPCols, HALF_>(r[c % kRB], wvc, relu_lo, radd, stg2, lane, flags, plain, out_box, ld_bytes, tmc, \
+                                        box_col0, trow, tma_pending, store_policy, a.debug)
           if ((c & 1) == 0) {
             if (epi == kEpiFull) KTF_STORE_BOX(kEpiFull, 0);
             else if (epi == kEpiAdd) KTF_STORE_BOX(kEpiAdd, 0);

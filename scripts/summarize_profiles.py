@@ -3,6 +3,7 @@
 
     python scripts/summarize_profiles.py launches gpurun_out/launches_r01.csv profiles/r01_launches.txt
     python scripts/summarize_profiles.py full gpurun_out/prof.ncu-rep profiles/r01_kernel_full.txt
+    python scripts/summarize_profiles.py traffic profiles/r02_traffic.json        (from the round-2 .ncu-rep files)
 """
 import collections
 import csv
@@ -69,5 +70,57 @@ def full(src, dst):
                     f.write(f"  {k:70s} {d[k][0]:>18s}\n")
 
 
+def _raw(src):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    res = []
+    for vals in rows[2:]:
+        d = dict(zip(hdr, zip(vals, units)))
+
+        def num(key, to):
+            v, u = d[key]
+            x = float(v.replace(",", ""))
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,
+                     "%": 1.0}.get(u, 1.0)
+            return x * scale
+        res.append({"kernel": d["Kernel Name"][0][:60],
+                    "dram_bytes": num("dram__bytes_read.sum", "byte") + num("dram__bytes_write.sum", "byte"),
+                    "us": num("gpu__time_duration.sum", "us"),
+                    "tensor_pct": num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "%")})
+    return res
+
+
+def traffic(dst, *_):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels, from the ncu --set full
+    captures of the bench commands; bench.py reads this file for roofline.traffic."""
+    import json
+    out = {}
+    fe = _raw("gpurun_out/prof_fe_r02.ncu-rep")[0]
+    out["frontend"] = {"kernel": fe["kernel"], "dram_bytes_per_launch": fe["dram_bytes"], "gpu_time_us": fe["us"],
+                       "source": "gpurun_out/prof_fe_r02.ncu-rep -> profiles/r02_frontend_ncu.txt (bench.py --workload "
+                                 "frontend, 1024 x 10 s)"}
+    pl = _raw("gpurun_out/prof_plda_r02.ncu-rep")[0]
+    out["plda_score"] = {"kernel": pl["kernel"], "dram_bytes_per_launch": pl["dram_bytes"], "gpu_time_us": pl["us"],
+                         "source": "gpurun_out/prof_plda_r02.ncu-rep -> profiles/r02_plda_score_ncu.txt (bench.py "
+                                   "--workload plda, first score GEMM of the step)"}
+    st = _raw("gpurun_out/prof_w2x_stack_r02.ncu-rep")
+    seen, per = set(), []
+    for k in st:                      # (ncu lists a kernel once per replayed section set: keep the first of each launch)
+        key = (k["kernel"], round(k["us"], 3))
+        if key in seen:
+            continue
+        seen.add(key)
+        per.append(k)
+    out["tdnn_stack"] = {"kernel": "gather_cmvn_splice_kernel + tdnn_tc_pair_kernel x5 + tdnn_tc_kernel<STATS> (one "
+                                   "wav2xvec step)",
+                         "dram_bytes_per_launch": sum(k["dram_bytes"] for k in per),
+                         "gpu_time_us": sum(k["us"] for k in per), "per_kernel": per,
+                         "source": "gpurun_out/prof_w2x_stack_r02.ncu-rep -> profiles/r02_wav2xvec_stack_ncu.txt (bench.py "
+                                   "default workload, 7 consecutive launches of one step)"}
+    with open(dst, "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
