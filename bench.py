@@ -618,8 +618,8 @@ def stage_plda(h, steps, warmup, n=50000):
     counts = [parallel.shard_range(n, r, h.world)[1] - parallel.shard_range(n, r, h.world)[0] for r in range(h.world)]
 
     def step(pairs):
-        # transforms + the only collective (all-gather of the transformed test vectors as per-rank async
-        # broadcasts, 25.6 MB in total) + the score GEMM of every arriving row block
+        # transforms + the only collective (ONE asynchronous NCCL all-gather of the transformed test vectors, 25.6 MB in
+        # total; the local rows are scored underneath it) + the score GEMMs of the other ranks' rows
         parallel.plda_score_sharded(layer, x_test, x_enroll, test_counts=counts, out=scores)
     ms, launches, clocks, _ = h.timed(step, steps, warmup)
 

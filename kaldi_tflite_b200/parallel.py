@@ -51,12 +51,14 @@ def gather_rows(local, counts=None):
 def exchange_test_vectors(u_test_local, test_counts=None):
     """
     The one collective of the PLDA path: all-gather of the transformed test vectors.
-    Returns (u_all, offsets, works): `works[r].wait()` makes the current stream wait for rank r's block.
+    Returns (u_all, offsets, works): `works[r].wait()` makes the current stream wait for rank r's block; `u_all` may be
+    read for block r only after that.
 
-    NCCL: ONE all-gather (`all_gather_into_tensor` on blocks padded to the largest shard -- shards from `shard_range`
-    differ by at most one row); 25.6 MB at 50 k x 128 is ~35 us of NVLink time, so a single collective beats per-rank
-    broadcasts, whose launch latencies add up (measured at 8 ranks: 0.63 ms for eight broadcasts).  Other backends
-    (gloo in the CPU / single-GPU tests) use one asynchronous broadcast per source rank.
+    NCCL: ONE asynchronous all-gather (`all_gather_into_tensor` on blocks padded to the largest shard -- shards from
+    `shard_range` differ by at most one row); 25.6 MB at 50 k x 128 is ~35 us of NVLink time, so a single collective
+    beats per-rank broadcasts, whose launch latencies add up (measured at 8 ranks: 0.63 ms for eight broadcasts).  It
+    runs on NCCL's own stream: the caller scores its LOCAL rows (and transforms its enrolled vectors) underneath it.
+    Other backends (gloo in the CPU / single-GPU tests) use one asynchronous broadcast per source rank.
     """
     rank, w = world()
     if test_counts is None:
@@ -72,14 +74,18 @@ def exchange_test_vectors(u_test_local, test_counts=None):
         per = max(int(c) for c in test_counts)
         if all(int(c) == per for c in test_counts):
             u_all = torch.empty((w * per, dim), device=u_test_local.device, dtype=u_test_local.dtype)
-            dist.all_gather_into_tensor(u_all, u_test_local.contiguous())
-        else:
-            padded = torch.zeros((per, dim), device=u_test_local.device, dtype=u_test_local.dtype)
-            padded[:u_test_local.shape[0]].copy_(u_test_local)
-            gathered = torch.empty((w * per, dim), device=u_test_local.device, dtype=u_test_local.dtype)
-            dist.all_gather_into_tensor(gathered, padded)
-            u_all = torch.cat([gathered[r * per:r * per + int(test_counts[r])] for r in range(w)], dim=0)
-        return u_all, offs, [_Done()] * w
+            work = dist.all_gather_into_tensor(u_all, u_test_local.contiguous(), async_op=True)
+            return u_all, offs, [_Gathered(work)] * w
+        padded = torch.zeros((per, dim), device=u_test_local.device, dtype=u_test_local.dtype)
+        padded[:u_test_local.shape[0]].copy_(u_test_local)
+        gathered = torch.empty((w * per, dim), device=u_test_local.device, dtype=u_test_local.dtype)
+        work = dist.all_gather_into_tensor(gathered, padded, async_op=True)
+        u_all = torch.empty((offs[-1], dim), device=u_test_local.device, dtype=u_test_local.dtype)
+
+        def compact():                        # ragged shards: drop the padding rows once the gather has landed
+            for r in range(w):
+                u_all[offs[r]:offs[r + 1]].copy_(gathered[r * per:r * per + int(test_counts[r])])
+        return u_all, offs, [_Gathered(work, compact)] * w
     u_all = torch.empty((offs[-1], dim), device=u_test_local.device, dtype=u_test_local.dtype)
     u_all[offs[rank]:offs[rank + 1]].copy_(u_test_local)
     works = [dist.broadcast(u_all[offs[r]:offs[r + 1]], src=r, async_op=True) if offs[r + 1] > offs[r] else None
@@ -87,10 +93,19 @@ def exchange_test_vectors(u_test_local, test_counts=None):
     return u_all, offs, works
 
 
-class _Done:
-    """Stand-in for a finished work handle (the NCCL all-gather is stream-ordered on the current stream)."""
+class _Gathered:
+    """Work handle of the single NCCL all-gather, shared by every rank's block: the first wait() makes the current stream
+    wait for the collective (and runs the optional compaction of ragged shards), later ones are free."""
+
+    def __init__(self, work, after=None):
+        self.work, self.after, self.done = work, after, False
 
     def wait(self):
+        if not self.done:
+            self.work.wait()
+            if self.after is not None:
+                self.after()
+            self.done = True
         return True
 
 
@@ -100,24 +115,34 @@ def plda_score_sharded(plda, x_test_local, x_enroll_local, test_counts=None, out
     x-vectors (raw, (n, dim) float32).  Returns this rank's block scores[all tests, local enrolled] -- test
     rows ordered by rank -- plus the gathered transformed test vectors.
 
-    The exchange is an all-gather of the transformed test vectors (`exchange_test_vectors`): one NCCL collective
-    followed by one score GEMM over all test rows; on backends without a GPU all-gather the per-rank
-    broadcasts are consumed block by block.  `test_counts` (rows per rank) saves the small size exchange when the caller already knows the
-    partition (e.g. from `shard_range`); `out` is an optional preallocated (n_test, n_enroll_local) score block.
+    The exchange is an all-gather of the transformed test vectors (`exchange_test_vectors`).  Over NCCL it
+    is one asynchronous collective: while it is in flight this rank transforms its enrolled vectors and scores its OWN
+    test rows, then the rows above and below them in two more score GEMMs.  On backends without a GPU all-gather the
+    per-rank broadcasts are consumed block by block.  `test_counts` (rows per rank) saves the small size exchange when
+    the caller already knows the partition (e.g. from `shard_range`); `out` is an optional preallocated
+    (n_test, n_enroll_local) score block.
     """
     rank, w = world()
     u_test_local = plda.transformVector(x_test_local.contiguous())
-    u_enroll_local = plda.transformVector(x_enroll_local.contiguous())
     if w == 1:
+        u_enroll_local = plda.transformVector(x_enroll_local.contiguous())
         return plda.logLikelihoodRatio(u_test_local, u_enroll_local, out=out), u_test_local
     u_all, offs, works = exchange_test_vectors(u_test_local, test_counts)
+    u_enroll_local = plda.transformVector(x_enroll_local.contiguous())
     if out is None:
         # row pitch padded to 16 bytes: the score kernel's boxed (TMA) stores need an aligned pitch
         ne = u_enroll_local.shape[0]
         out = torch.empty((offs[-1], (ne + 7) // 8 * 8), device=u_test_local.device, dtype=u_test_local.dtype)[:, :ne]
     scores = out
-    if all(isinstance(wk, _Done) for wk in works):
-        plda.logLikelihoodRatio(u_all, u_enroll_local, out=scores)      # one collective, one score GEMM
+    if all(isinstance(wk, _Gathered) for wk in works):
+        lo, hi = offs[rank], offs[rank + 1]
+        if hi > lo:                           # local rows: no need to wait for anybody
+            plda.logLikelihoodRatio(u_test_local, u_enroll_local, out=scores[lo:hi])
+        works[0].wait()
+        if lo > 0:
+            plda.logLikelihoodRatio(u_all[:lo], u_enroll_local, out=scores[:lo])
+        if offs[-1] > hi:
+            plda.logLikelihoodRatio(u_all[hi:], u_enroll_local, out=scores[hi:])
         return scores, u_all
     for r in range(w):
         if works[r] is None:
