@@ -64,5 +64,19 @@ def like_input(out, ref):
     return out.cpu().numpy()
 
 
+_uniform_offsets = {}
+
+
 def uniform_offsets(batch, rows):
-    return torch.arange(batch + 1, device=device(), dtype=torch.int64) * rows
+    """offsets[b] = b * rows on the device; cached per (device, batch, rows) -- treat as read-only."""
+    dev = device()
+    key = (str(dev), int(batch), int(rows))
+    t = _uniform_offsets.get(key)
+    if t is None:
+        t = torch.arange(batch + 1, device=dev, dtype=torch.int64) * rows
+        # (a tensor first produced while a CUDA graph is being captured is only filled when the graph runs: never cache it)
+        if not (dev.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+            if len(_uniform_offsets) > 64:
+                _uniform_offsets.clear()
+            _uniform_offsets[key] = t
+    return t

@@ -114,16 +114,16 @@ class XvectorExtractor:
             # tcgen05 stack: gather -> CMVN -> splice is ONE pre-pass kernel in front of the GEMMs; the kept rows are
             # never written as a gathered / normalised fp32 matrix
             _, voffs, index = self.vad.compact_ragged(feats, mask, offsets, gather=False)
-            self._no_voiced = (voffs[1:] == voffs[:-1]).any()
+            self._voffs = voffs                # examined only when the result leaves as a host array (see __call__)
             mf = feats.shape[0] if max_frames is None else max_frames
             emb = stack.forward_vad(feats, index, voffs, mf, self.cmvn.N)
             return emb, mask, voffs
         # `voiced` keeps the upper-bound row count; the kept-row count stays on the device (voffs[-1])
         voiced, voffs, _ = self.vad.compact_ragged(feats, mask, offsets, gather=True)
         # An utterance without voiced frames has no statistics to pool (the reference's gather_nd / reduce_mean
-        # would produce NaN).  The flag stays on the device -- checking it here would stall the launch queue --
-        # and is examined when the result is handed back as a host array (see __call__).
-        self._no_voiced = (voffs[1:] == voffs[:-1]).any()
+        # would produce NaN).  The offsets stay on the device -- checking them here would stall the launch queue --
+        # and are examined when the result is handed back as a host array (see __call__).
+        self._voffs = voffs
         normed, _ = self.cmvn.forward_ragged(voiced, voffs, max_frames=max_frames)
         emb, _ = self.xvec.forward_ragged(normed, voffs)
         return emb, mask, voffs
@@ -168,7 +168,7 @@ class XvectorExtractor:
         y = self.backend(emb)
         ref = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
         out = T.like_input(y.squeeze(), ref)                      # tf.squeeze (:184)
-        if not isinstance(out, torch.Tensor) and bool(self._no_voiced.item()):
+        if not isinstance(out, torch.Tensor) and bool((self._voffs[1:] == self._voffs[:-1]).any().item()):
             raise ValueError("an utterance has no voiced frames after VAD")
         if return_intermediate:
             return out, {"mfcc": feats, "frame_offsets": offsets, "mask": mask,
