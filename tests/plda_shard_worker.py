@@ -1,8 +1,10 @@
 """
-One rank of the two-rank sharded PLDA parity test (tests/test_gpu_round2.py).  Both ranks share cuda:0 (NCCL refuses
-two ranks on one device, so gloo carries the CUDA tensors of the exchange); every rank scores its shard of the ENROLLED
-columns with the real kernels through kaldi_tflite_b200.parallel.plda_score_sharded and checks its
-(n_test x n_enroll / G) block against the float64 oracle: |delta| <= 1e-3 * max(|s|, 1).
+One rank of the two-rank sharded PLDA parity test (tests/test_gpu_round2.py).  Default: both ranks share cuda:0 (NCCL
+refuses two ranks on one device, so gloo carries the CUDA tensors of the exchange).  With `nccl` as the second argument
+every rank takes its own GPU and the exchange is the asynchronous NCCL all-gather (the third argument is the number of
+test vectors: an odd count makes the shards ragged).  Every rank scores its shard of the ENROLLED columns with the real
+kernels through kaldi_tflite_b200.parallel.plda_score_sharded and checks its (n_test x n_enroll / G) block against the
+float64 oracle: |delta| <= 1e-3 * max(|s|, 1).
 """
 
 import json
@@ -18,16 +20,16 @@ import torch
 import torch.distributed as dist
 
 
-def main(out_dir):
+def main(out_dir, backend="gloo", n_test=1500):
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(0)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank if backend == "nccl" else 0)
+    dist.init_process_group(backend, rank=rank, world_size=world)
     import kaldi_tflite_b200 as ktf
     from kaldi_tflite_b200 import parallel
     from oracle import ktf_oracle as O
     from test_gpu_tdnn_plda import synthetic_plda
 
-    dim, n_test, n_enroll = 128, 1500, 1100            # ragged against the 128 x 256 tiles and against the ranks
+    dim, n_enroll = 128, 1100                          # ragged against the 128 x 256 tiles and against the ranks
     mean, Tm, psi = synthetic_plda(dim)
     rng = np.random.default_rng(31)
     x = rng.standard_normal((n_test + n_enroll, dim))
@@ -58,4 +60,4 @@ def main(out_dir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], *(sys.argv[2:3]), *(int(a) for a in sys.argv[3:4]))

@@ -408,13 +408,13 @@ def test_dither_in_kernel_is_per_framed_sample(ktf):
 # sharded PLDA, two ranks on one GPU
 # ------------------------------------------------------------------------------------------------
 
-def test_plda_sharded_two_ranks_vs_oracle(tmp_path):
+def _run_shard_workers(tmp_path, extra=()):
     worker = os.path.join(ROOT, "tests", "plda_shard_worker.py")
-    port = 29500 + (os.getpid() % 2000)
+    port = 29500 + (os.getpid() % 2000) + len(extra)
     procs = []
     for rank in range(2):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-        procs.append(subprocess.Popen([sys.executable, worker, str(tmp_path)], env=env, stdout=subprocess.PIPE,
+        procs.append(subprocess.Popen([sys.executable, worker, str(tmp_path), *extra], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for rank, (p, o) in enumerate(zip(procs, outs)):
@@ -425,6 +425,20 @@ def test_plda_sharded_two_ranks_vs_oracle(tmp_path):
         assert r["ok"], r
         assert r["max_rel"] <= 1e-3, r
         assert r["launches"] > 0
+
+
+def test_plda_sharded_two_ranks_vs_oracle(tmp_path):
+    _run_shard_workers(tmp_path)
+
+
+def test_plda_sharded_two_gpus_nccl_async_allgather(tmp_path):
+    """The NCCL path of parallel.plda_score_sharded: ONE asynchronous all-gather, the local rows scored underneath it;
+    even shards (1500 test vectors) and ragged ones (1501: padded gather + compaction).  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run_shard_workers(tmp_path, ("nccl", "1500"))
+    _run_shard_workers(tmp_path, ("nccl", "1501"))
 
 
 def _run_cabi_workers(tmp_path, nranks):
