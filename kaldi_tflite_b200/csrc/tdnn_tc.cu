@@ -2286,7 +2286,8 @@ static int stack_forward_impl(ktf_tdnn_stack* s, const float* feats_dev, const i
       const unsigned grid = blocks_for(prow * (ld >> 3), 256);
       if (i == 0 && pre != nullptr) {
         // VAD gather + sliding CMVN + splice in one pass (the rows never exist as a gathered / normalised fp32 matrix)
-        const long long gys = (pre->max_frames + 255) / 256;
+        static const int tc_target = getenv("KTF_PREPASS_TC") ? std::max(atoi(getenv("KTF_PREPASS_TC")), 32) : 256;
+        const long long gys = (pre->max_frames + tc_target - 1) / tc_target;
         const int tc = (int)((((pre->max_frames + gys - 1) / gys) + 1) & ~1LL);
         const size_t smem = prepass_smem_bytes(tc, pre->cmvn_window, L.D);
         KTF_CHECK_ARG(smem <= 113 * 1024 && gys <= 65535, "CMVN window %d x dim %d does not fit the fused pre-pass",
