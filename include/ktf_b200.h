@@ -373,6 +373,14 @@ enum { KTF_SCORES_NATIVE = 0, KTF_SCORES_BF16 = 1 };
 int ktf_plda_score_ex(const ktf_plda* p, const void* u_test_dev, int64_t n_test, const void* u_enroll_dev,
                       int64_t n_enroll, void* scores_dev, int64_t ld, int32_t score_format, void* stream);
 
+/* Best trial per test vector (the top-k = 1 form of the compact output): best_score_dev[i] =
+ * max_j LLR(test u_i | enrolled u_j) and best_index_dev[i] = the j that attains it (the lowest j on a tie; -1 and -inf
+ * when n_enroll == 0), with the same fp32-equivalent arithmetic as the score matrix entry (plda.py:215-245) -- the
+ * (n_test, n_enroll) matrix is never written, so the call is bound by the operand stream instead of a 4-byte-per-trial
+ * HBM write.  Needs a float32 handle (the tcgen05 score GEMM). */
+int ktf_plda_score_top1(const ktf_plda* p, const void* u_test_dev, int64_t n_test, const void* u_enroll_dev,
+                        int64_t n_enroll, float* best_score_dev, int64_t* best_index_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

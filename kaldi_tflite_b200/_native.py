@@ -104,6 +104,7 @@ _SIGNATURES = {
     "ktf_plda_transform": (c_int32, [_P, _P, c_int64, _P, _P]),
     "ktf_plda_score": (c_int32, [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P]),
     "ktf_plda_score_ex": (c_int32, [_P, _P, c_int64, _P, c_int64, _P, c_int64, c_int32, _P]),
+    "ktf_plda_score_top1": (c_int32, [_P, _P, c_int64, _P, c_int64, _P, _P, _P]),
 }
 
 _lib = None

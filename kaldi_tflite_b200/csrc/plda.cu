@@ -139,8 +139,21 @@ __global__ void plda_split_kernel(const float* __restrict__ u, long long n, int 
   }
 }
 
+// Decodes the best-entry keys of tc_gemm_nt(row_best): score and column of every test row (-1: no enrolled vector).
+__global__ void plda_top1_decode_kernel(const unsigned long long* __restrict__ keys, long long n,
+                                        float* __restrict__ score, long long* __restrict__ index) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = keys[i];
+  const unsigned u = (unsigned)(key >> 32);
+  const unsigned bits = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  score[i] = key ? __uint_as_float(bits) : -INFINITY;
+  index[i] = key ? (long long)(0xffffffffu - (unsigned)(key & 0xffffffffull)) : -1;
+}
+
+// top1_score / top1_index non-null: no score matrix, the best enrolled column of every test row instead.
 int score_tc(const ktf_plda* p, const float* ut, int64_t nt, const float* ue, int64_t ne, void* scores, int64_t ld,
-             int scores_bf16, cudaStream_t st) {
+             int scores_bf16, cudaStream_t st, float* top1_score = nullptr, long long* top1_index = nullptr) {
   const int dim = p->dim;
   const long long K = 3LL * dim;
   ktf::Carver cv;
@@ -148,6 +161,7 @@ int score_tc(const ktf_plda* p, const float* ut, int64_t nt, const float* ue, in
   const size_t o_b = cv.take((size_t)ne * K * sizeof(__half));
   const size_t o_ai = cv.take((size_t)nt * sizeof(float));
   const size_t o_bj = cv.take((size_t)ne * sizeof(float));
+  const size_t o_key = cv.take(top1_score ? (size_t)nt * sizeof(unsigned long long) : 0);
   int rc = p->ws.ensure(cv.off);
   if (rc != KTF_OK) return rc;
   char* base = static_cast<char*>(p->ws.ptr);
@@ -167,7 +181,14 @@ int score_tc(const ktf_plda* p, const float* ut, int64_t nt, const float* ue, in
   KTF_LAUNCH_OK();
   plda_split_kernel<<<blocks(ne * dim), 256, 0, st>>>(ue, ne, dim, nullptr, 1, Bs);
   KTF_LAUNCH_OK();
-  return ktf::tc_gemm_nt(As, nt, K, Bs, ne, K, K, /*fp16=*/1, Ai, Bj, scores, ld, scores_bf16, st);
+  if (top1_score == nullptr)
+    return ktf::tc_gemm_nt(As, nt, K, Bs, ne, K, K, /*fp16=*/1, Ai, Bj, scores, ld, scores_bf16, st);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + o_key);
+  KTF_CUDA(cudaMemsetAsync(keys, 0, (size_t)nt * sizeof(unsigned long long), st));
+  if ((rc = ktf::tc_gemm_nt(As, nt, K, Bs, ne, K, K, /*fp16=*/1, Ai, Bj, nullptr, ne, 0, st, keys)) != KTF_OK) return rc;
+  plda_top1_decode_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(keys, nt, top1_score, top1_index);
+  KTF_LAUNCH_OK();
+  return KTF_OK;
 }
 
 template <typename T>
@@ -316,6 +337,16 @@ int ktf_plda_score_ex(const ktf_plda* p, const void* u_test_dev, int64_t n_test,
                     (cudaStream_t)stream);
   }
   return ktf_plda_score(p, u_test_dev, n_test, u_enroll_dev, n_enroll, scores_dev, ld, stream);
+}
+
+int ktf_plda_score_top1(const ktf_plda* p, const void* u_test_dev, int64_t n_test, const void* u_enroll_dev,
+                        int64_t n_enroll, float* best_score_dev, int64_t* best_index_dev, void* stream) {
+  KTF_CHECK_ARG(p && u_test_dev && u_enroll_dev && best_score_dev && best_index_dev, "ktf_plda_score_top1: null argument");
+  KTF_CHECK_ARG(p->use_tc, "ktf_plda_score_top1 needs a float32 PLDA handle on an sm_100 device");
+  KTF_CHECK_ARG(n_enroll < (1LL << 32), "ktf_plda_score_top1: more than 2^32 enrolled vectors");
+  if (n_test <= 0) return KTF_OK;
+  return score_tc(p, (const float*)u_test_dev, n_test, (const float*)u_enroll_dev, n_enroll, nullptr, n_enroll, 0,
+                  (cudaStream_t)stream, best_score_dev, (long long*)best_index_dev);
 }
 
 int ktf_plda_score(const ktf_plda* p, const void* u_test_dev, int64_t n_test, const void* u_enroll_dev,

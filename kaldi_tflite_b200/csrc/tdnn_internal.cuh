@@ -23,8 +23,10 @@ int stats_sums_f32(const float* y_dev, const int64_t* offsets_dev, int64_t batch
                    cudaStream_t st);
 // tcgen05 engine as a plain "NT" GEMM: C[i, j] = sum_k A[i, k] * B[j, k] + row_add[i] + col_add[j];
 // A (m, K), B (n, K) row-major 16-bit (bf16, or fp16 when fp16 != 0), C fp32 or (c_bf16 != 0) bf16, row stride ldc
-// elements.
+// elements.  With `row_best` (m zero-initialised 64-bit keys) nothing is stored (C may be null): every row keeps its best
+// entry as a key -- order-preserving float bits << 32 | (0xffffffff - column), maximised atomically; the lowest column
+// wins a tie.
 int tc_gemm_nt(const void* A, long long m, long long lda, const void* B, long long n, long long ldb, long long K,
                int fp16, const float* row_add, const float* col_add, void* C, long long ldc, int c_bf16,
-               cudaStream_t st);
+               cudaStream_t st, unsigned long long* row_best = nullptr);
 }  // namespace ktf

@@ -101,6 +101,8 @@ struct TcArgs {
   int debug;                // development knobs (KTF_TC_DEBUG): 1 = skip global stores, 2 = skip the epilogue math,
                             // 4 = stage the boxes but never issue their stores
   long long* trace;         // development (KTF_TC_TRACE=file): clock64 of cluster 0's tile phases, 4 slots per tile
+  unsigned long long* row_best;   // pair kernel, optional: instead of storing C, keep the best entry of every row as an
+                                  // atomically maximised key (order-preserving float bits << 32 | ~column), see top1_key
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -380,6 +382,13 @@ __device__ __forceinline__ void store_chunk(const unsigned (&r)[32], const float
 //      kEpiAdd   y = (acc + bias) + row addend                  (PLDA scoring: nothing to clamp)
 // all three round like the general form with scale 1 / offset 0 / lo = -FLT_MAX, so every path gives the same fp32 value.
 constexpr int kEpiFull = 0, kEpiLean = 1, kEpiAdd = 2;
+
+// Key of (value, column) whose unsigned order is: larger value first, then SMALLER column.  0 never occurs for a real value.
+__device__ __forceinline__ unsigned long long top1_key(float v, int col) {
+  const unsigned b = __float_as_uint(v);
+  const unsigned u = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)col);
+}
 constexpr int kBoxRow = 128;                         // bytes per staged row of a box
 constexpr int kBoxBytes = 32 * kBoxRow;
 
@@ -1153,12 +1162,34 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // load latency and 96 registers per thread: one buffer
       constexpr int kRB = EW == 16 ? 1 : 2;
       unsigned r[kRB][32];
+      float best_v = -INFINITY;                  // (row_best launches) best entry of this row among the warp's columns
+      int best_c = -1;
       tmem_ld32_issue(taddr0, r[0]);
 #pragma unroll
       for (int c = 0; c < kPChunks; ++c) {
         tmem_ld_wait(r[c % kRB]);
         if (kRB == 2 && c + 1 < kPChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[(c + 1) % kRB]);
         const int col0 = col_base + colq * kPCols + c * 32;
+        if (a.row_best != nullptr) {
+          // compact output: nothing is stored, the row keeps its best entry -- the add-only form of the epilogue, columns
+          // in ascending order and a strict comparison, so the lowest column wins a tie
+          const float4* b4 = reinterpret_cast<const float4*>(wv + c * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bb = b4[q];
+            const float v0 = (__uint_as_float(r[c % kRB][4 * q + 0]) + bb.x) + radd;
+            const float v1 = (__uint_as_float(r[c % kRB][4 * q + 1]) + bb.y) + radd;
+            const float v2 = (__uint_as_float(r[c % kRB][4 * q + 2]) + bb.z) + radd;
+            const float v3 = (__uint_as_float(r[c % kRB][4 * q + 3]) + bb.w) + radd;
+            const int cq = col0 + 4 * q;
+            if (cq + 0 < n_cols && v0 > best_v) { best_v = v0; best_c = cq + 0; }
+            if (cq + 1 < n_cols && v1 > best_v) { best_v = v1; best_c = cq + 1; }
+            if (cq + 2 < n_cols && v2 > best_v) { best_v = v2; best_c = cq + 2; }
+            if (cq + 3 < n_cols && v3 > best_v) { best_v = v3; best_c = cq + 3; }
+          }
+          if (kRB == 1 && c + 1 < kPChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[0]);
+          continue;
+        }
         // the 128-byte box this chunk belongs to: the chunk itself (fp32 rows) or a pair of chunks (bf16 rows)
         const int box_col0 = kBf16 ? col_base + colq * kPCols + (c & ~1) * 32 : col0;
         constexpr int kBoxCols = kBoxRow / kEs;
@@ -1196,6 +1227,7 @@ tdnn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (kRB == 1 && c + 1 < kPChunks) tmem_ld32_issue(taddr0 + (unsigned)((c + 1) * 32), r[0]);
       }
+      if (a.row_best != nullptr && best_c >= 0 && row < m_rows) atomicMax(a.row_best + row, top1_key(best_v, best_c));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -2097,7 +2129,7 @@ int affine_tc_forward(const ktf_affine* a, const float* x_dev, const int64_t* in
 // (bf16 or fp16), C fp32 with row stride ldc.  K and both leading dimensions must be multiples of 8.
 int tc_gemm_nt(const void* A, long long m, long long lda, const void* B, long long n, long long ldb, long long K,
                int fp16, const float* row_add, const float* col_add, void* C, long long ldc, int c_bf16,
-               cudaStream_t st) {
+               cudaStream_t st, unsigned long long* row_best) {
   int rc = check_arch();
   if (rc != KTF_OK) return rc;
   CUtensorMap tmA, tmB;
@@ -2115,12 +2147,13 @@ int tc_gemm_nt(const void* A, long long m, long long lda, const void* B, long lo
   args.row_add = row_add;
   args.out = C;
   args.out_ld = ldc;
+  args.row_best = row_best;
   // streaming output (PLDA: the score matrix), operands re-read by every tile: see TcArgs::l2_stream_out
   args.l2_stream_out = ((double)m * (double)n * (c_bf16 ? 2.0 : 4.0) > 64e6) ? 1 : 0;
   if (const char* e = getenv("KTF_TC_L2_HINTS")) args.l2_stream_out = atoi(e);
   args.group_m = (n + BN - 1) / BN > 8 ? 32 : 0;     // (measured at 50 000^2: 1 -> 2.77, 8 -> 2.61, 16 -> 2.54, 32 -> 2.47-2.51, 64 -> 2.65 ms)
   if (const char* e = getenv("KTF_TC_GROUP_M")) args.group_m = atoi(e);
-  if (pair_enabled()) {
+  if (pair_enabled() || row_best != nullptr) {    // (the best-entry epilogue exists in the pair kernel only)
     CUtensorMap tmBh;
     if ((rc = encode_map(&tmBh, B, (unsigned long long)K, (unsigned long long)n, (unsigned long long)ldb, BK, BN / 2)) != KTF_OK)
       return rc;

@@ -128,6 +128,21 @@ class PLDA(Layer):
                                           N.KTF_SCORES_BF16 if compact else N.KTF_SCORES_NATIVE, T.stream_ptr()))
         return out
 
+    def bestMatch(self, u_test, u_enroll=None, num_examples=1.0):
+        """Best enrolled vector per test vector: (scores (n_test,) float32, indexes (n_test,) int64) with
+        scores[i] = max_j LLR(test i | enrolled j) -- the entry of `logLikelihoodRatio` (plda.py:215-245), same
+        arithmetic -- without writing the (n_test, n_enroll) matrix (top-k = 1; float32 layers only).
+        The lowest index wins a tie."""
+        if self.paramDtype != np.float32:
+            raise ValueError("bestMatch needs a float32 PLDA layer")
+        u_enroll = u_test if u_enroll is None else u_enroll
+        nt, ne = u_test.shape[0], u_enroll.shape[0]
+        best = torch.empty((nt,), device=u_test.device, dtype=torch.float32)
+        index = torch.empty((nt,), device=u_test.device, dtype=torch.int64)
+        N.check(N.lib().ktf_plda_score_top1(self.handle_for(num_examples), T.ptr(u_test), nt, T.ptr(u_enroll), ne,
+                                            T.ptr(best), T.ptr(index), T.stream_ptr()))
+        return best, index
+
     def call(self, inputs):
         x = T.as_device(inputs)
         self._maybe_build(x.shape)

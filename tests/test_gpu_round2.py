@@ -497,6 +497,41 @@ def test_plda_compact_bf16_scores(ktf):
 # VAD at scale
 # ------------------------------------------------------------------------------------------------
 
+def test_plda_best_match_equals_score_matrix(ktf):
+    """SURVEY 8f rank 3, top-k = 1: ktf_plda_score_top1 / PLDA.bestMatch returns, per test vector, the maximum of the score
+    matrix row and the column that attains it -- same arithmetic as the matrix entry (bit-equal), no matrix written --
+    and that column is the float64 oracle's best within the 1e-3 score tolerance."""
+    import torch
+    from test_gpu_tdnn_plda import synthetic_plda
+    dim = 128
+    mean, Tm, psi = synthetic_plda(dim)
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((1037 + 700, dim))
+    x = (x / np.linalg.norm(x, axis=1, keepdims=True) * np.sqrt(dim)).astype(np.float32)
+    layer = ktf.layers.PLDA(dim, mean, Tm, psi, dtype=np.float32, return_transformed=False)
+    u = layer.transformVector(torch.from_numpy(x).cuda())
+    ut, ue = u[:1037].contiguous(), u[1037:].contiguous()
+    n0 = ktf.launch_count()
+    best, index = layer.bestMatch(ut, ue)
+    assert ktf.launch_count() > n0
+    full = layer.logLikelihoodRatio(ut, ue)
+    torch.cuda.synchronize()
+    want = full.max(dim=1).values
+    assert torch.equal(best, want)
+    assert int(index.min()) >= 0 and int(index.max()) < 700
+    assert torch.equal(full[torch.arange(1037, device=full.device), index], want)
+    uo = O.plda_transform(x, mean, Tm, psi, dtype=np.float64)
+    ref = O.plda_llr(uo, psi)[:1037, 1037:]
+    at = ref[np.arange(1037), index.cpu().numpy()]
+    assert np.all(ref.max(axis=1) - at <= 1e-3 * np.maximum(np.abs(ref.max(axis=1)), 1.0))
+    # all-vs-all on one set (the reference's call()): every vector's best match is found in the same set
+    best2, index2 = layer.bestMatch(ut)
+    full2 = layer.logLikelihoodRatio(ut)
+    torch.cuda.synchronize()
+    assert torch.equal(best2, full2.max(dim=1).values)
+    assert torch.equal(full2[torch.arange(1037, device=full2.device), index2], best2)
+
+
 def test_vad_exact_at_one_million_frames(ktf):
     """1024 utterances x 998 frames (BASELINE config 4 shard): the kernel accumulates the per-utterance mean in fp64,
     the oracle in pairwise fp32; the masks must still agree bit for bit on MFCCs of gated noise.  Frames within 1 ulp
