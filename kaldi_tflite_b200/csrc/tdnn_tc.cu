@@ -7,23 +7,23 @@
 //
 //   y[r, u] = scale[u] * relu( sum_k sum_d x[r + ctx_k, d] * W[u, k*D + d] + bias[u] ) + offset[u]
 //
-//   * operands 16-bit (bf16 for the TDNN, fp16 hi/lo splits for PLDA), accumulation fp32 in TMEM
-//     (tcgen05.mma.cta_group::1.kind::f16, M128 x N256 x K16);
+//   * operands 16-bit (bf16 for the TDNN, fp16 hi/lo splits for PLDA), accumulation fp32 in TMEM (tcgen05.mma kind::f16);
 //   * the frame splice is IMPLICIT: tap k is a TMA box load of the activation matrix shifted by ctx_k
 //     rows -- the (B, T, K, D) gathered tensor of the reference is never built;
 //   * edge clamping (tdnn.py:244-247) is provided by the activation layout: every utterance carries
 //     kHalo replicated rows on both sides ("padded rows"); the epilogue of each layer writes the halo
 //     replicas the next layer's taps need and skips the halo rows of its own tile;
-//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
-//     warps 2..9 = epilogue (two warps per TMEM lane quarter, each owning 128 of the tile's columns; TMEM
-//     loads run one chunk ahead; rows are transposed through a per-warp smem buffer so that global stores
-//     cover full 32-byte sectors, 64 contiguous bytes per row);
-//   * 4-stage smem ring (48 KB per stage) between TMA and MMA, 2 accumulator stages of 256 TMEM columns
-//     between MMA and epilogue, persistent CTAs (one per SM);
-//   * three epilogues: bf16 rows (next layer's operand), fp32 rows (+ per-row / per-column addends:
-//     PLDA's A_i + B_j), and STATS: the layer that feeds StatsPooling runs with the operands swapped
-//     (M = units, N = frames), so a thread owns ONE unit and walks the frames of the tile in its own
-//     registers -- per-utterance sum / sum-of-squares need no cross-thread reduction and the widest
+//   * two kernels share the helpers.  tdnn_tc_pair_kernel (row-storing layers, PLDA scoring): clusters of two CTAs
+//     compute 256 x 256 tiles with cta_group::2 (each CTA owns 128 rows and loads half of B), 8 or 16 epilogue warps,
+//     a 5- or 4-stage ring of 32 KB k-blocks, rows leave as 32-row x 128-byte TMA store boxes.  tdnn_tc_kernel
+//     (single CTA, M128 x N256 x K16, 4-stage ring of 48 KB): the STATS layer, and every launch under KTF_TC_PAIR=0;
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator, the others = epilogue
+//     (a thread owns one accumulator row: TMEM load -> per-column vectors -> staging -> boxed / per-row store);
+//   * 2 accumulator stages of 256 TMEM columns between MMA and epilogue, persistent CTAs (one per SM);
+//   * three outputs: bf16 rows (next layer's operand), fp32 rows (+ per-row / per-column addends:
+//     PLDA's A_i + B_j; optionally only the best entry per row), and STATS: the layer that feeds StatsPooling runs
+//     with the operands swapped (M = units, N = frames), so a thread owns ONE unit and walks the frames of the tile in
+//     its own registers -- per-utterance sum / sum-of-squares need no cross-thread reduction and the widest
 //     activation of the network (frames x 1500) is never written to HBM.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -480,7 +480,7 @@ __device__ __forceinline__ void store_box(const unsigned (&r)[32], const float* 
 }
 
 // Ragged / unaligned chunk of the pair kernel (right edge of the matrix, output pitch not a multiple of 16 bytes): fp32
-// staging, bounds-checked scalar stores with the per-row flags.  Same arithmetic (and association) as store_chunk2.
+// staging, bounds-checked scalar stores with the per-row flags.  Same arithmetic (and association) as store_box.
 template <bool OUT_BF16, int VSTRIDE>
 __device__ __forceinline__ void store_chunk_ragged(const unsigned (&r)[32], const float* vb, bool lean, float relu_lo,
                                                    float radd, unsigned char* stg, int lane, int flags, unsigned char* out0,
