@@ -189,3 +189,23 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in d, key
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_committed_traffic_summary_feeds_the_bench_roofline():
+    """bench.py takes roofline.traffic (DRAM bytes per launch of the dominant kernel) from profiles/r02_traffic.json, which
+    scripts/summarize_profiles.py writes from the ncu --set full captures: the file must carry the three kernels the
+    bench asks for, and the per-kernel breakdown of the stack must add up."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ktf_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for key in ("frontend", "plda_score", "tdnn_stack"):
+        traffic, src = bench.measured_traffic(key)
+        assert traffic and traffic > 1e6, key
+        assert "profiles/r02_traffic.json" in src
+    with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+        d = json.load(f)
+    per = d["tdnn_stack"]["per_kernel"]
+    assert len(per) == 7
+    assert abs(sum(k["dram_bytes"] for k in per) - d["tdnn_stack"]["dram_bytes_per_launch"]) < 1.0
+    assert bench.measured_traffic("no such kernel") == (None, None)
